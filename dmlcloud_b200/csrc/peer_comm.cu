@@ -1,0 +1,296 @@
+// Fused gradient-bucket all-reduce over NVLink 5 / NVSwitch peer memory (sm_100a).
+//
+// Replaces, for one DDP bucket, the chain the reference runs through torch (pipeline.py:74 -> Reducer -> c10d):
+//     bucket * (1/W)  [-> bf16]   ->   allreduce(SUM)   ->   [bf16 ->] fp32 copy back into .grad
+// with ONE kernel: scale+cast into this rank's staging half (K1), flag barrier through peer-mapped memory, rank-ordered
+// fp32 sum over every rank's staging read across NVLink (the collective), write-back into the fp32 bucket (K2), plus
+// an optional fused sum of squares for gradient clipping.  No NCCL, no host round trip, CUDA-graph capturable (the
+// sequence number lives in device memory).
+//
+//   one-shot  (message <= oneshot_max):  every rank reads all W staging buffers  — (W-1)*M bytes over NVLink per GPU,
+//                                        one barrier; latency-optimal for the 41 KB MNIST bucket.
+//   two-shot  (larger):                  reduce-scatter then all-gather through peer memory — 2*(W-1)/W*M bytes per
+//                                        GPU, two barriers; bandwidth-optimal for ResNet-18's 1.96/27.5/15.1 MiB buckets.
+//
+// Numerics: fp32 accumulate in rank order 0..W-1 on every rank => results are bit-identical across ranks and equal to
+// oracle/grad_oracle.py allreduce_f32 / allreduce_bf16.  Two-shot with the bf16 wire rounds the sum to bf16 for the
+// all-gather phase (same as an NCCL bf16 all-reduce); the fp32 wire is exact in both algorithms.
+#include <new>
+
+#include "peer_comm.cuh"
+
+namespace dmlb {
+
+template <int kWire>
+struct Wire;
+
+template <>
+struct Wire<DMLB_WIRE_F32> {  // 4 elements per 16-byte wire vector
+    static constexpr int kElems = 4;
+    __device__ static __forceinline__ uint4 pack(const float *v) {
+        uint4 o;
+        o.x = __float_as_uint(v[0]), o.y = __float_as_uint(v[1]), o.z = __float_as_uint(v[2]), o.w = __float_as_uint(v[3]);
+        return o;
+    }
+    __device__ static __forceinline__ void accumulate(float *acc, uint4 w) {
+        acc[0] += __uint_as_float(w.x), acc[1] += __uint_as_float(w.y);
+        acc[2] += __uint_as_float(w.z), acc[3] += __uint_as_float(w.w);
+    }
+};
+
+template <>
+struct Wire<DMLB_WIRE_BF16> {  // 8 elements per 16-byte wire vector
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ uint4 pack(const float *v) {
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]), o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]), o.w = pack_bf16x2(v[6], v[7]);
+        return o;
+    }
+    __device__ static __forceinline__ void accumulate(float *acc, uint4 w) {
+        acc[0] += bf16_lo(w.x), acc[1] += bf16_hi(w.x), acc[2] += bf16_lo(w.y), acc[3] += bf16_hi(w.y);
+        acc[4] += bf16_lo(w.z), acc[5] += bf16_hi(w.z), acc[6] += bf16_lo(w.w), acc[7] += bf16_hi(w.w);
+    }
+};
+
+// load kElems fp32 bucket elements of wire vector g (guarded at the ragged end), scaled
+template <int E>
+__device__ __forceinline__ void load_bucket(const float *bucket, size_t g, size_t n, float scale, float *v) {
+    const size_t e0 = g * E;
+    if (e0 + E <= n) {
+#pragma unroll
+        for (int j = 0; j < E; j += 4) {
+            float4 t = *reinterpret_cast<const float4 *>(bucket + e0 + j);
+            v[j] = t.x * scale, v[j + 1] = t.y * scale, v[j + 2] = t.z * scale, v[j + 3] = t.w * scale;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = (e0 + j < n) ? bucket[e0 + j] * scale : 0.0f;
+    }
+}
+
+template <int E>
+__device__ __forceinline__ double store_bucket(float *bucket, size_t g, size_t n, const float *v, bool sumsq) {
+    const size_t e0 = g * E;
+    double p = 0.0;
+    if (e0 + E <= n) {
+#pragma unroll
+        for (int j = 0; j < E; j += 4)
+            *reinterpret_cast<float4 *>(bucket + e0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (sumsq) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) p += (double)v[j] * v[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+            if (e0 + j < n) {
+                bucket[e0 + j] = v[j];
+                if (sumsq) p += (double)v[j] * v[j];
+            }
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// one-shot
+// ---------------------------------------------------------------------------------------------------------------------
+template <int kWire>
+__global__ void __launch_bounds__(kCommThreads, 2)
+allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, float scale, double *sumsq_out) {
+    typedef Wire<kWire> W;
+    constexpr int E = W::kElems;
+    const uint32_t s = comm_begin(c);
+    const int half = s & 1;
+    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = min(nvec, lo + per);
+
+    uint4 *mine = reinterpret_cast<uint4 *>(c.stage(c.rank, half));
+    for (size_t g = lo + threadIdx.x; g < hi; g += kCommThreads) {
+        float v[E];
+        load_bucket<E>(bucket, g, n, scale, v);
+        mine[g] = W::pack(v);
+    }
+    comm_barrier(c, 0, s);
+
+    double part = 0.0;
+    for (size_t g = lo + threadIdx.x; g < hi; g += kCommThreads) {
+        uint4 w[DMLB_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+            if (r < c.world) w[r] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.stage(r, half)) + g);
+        float acc[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+            if (r < c.world) W::accumulate(acc, w[r]);
+        part += store_bucket<E>(bucket, g, n, acc, sumsq_out != nullptr);
+    }
+    if (sumsq_out) {
+        double tot = block_sum(part);
+        if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
+    }
+    comm_end(c, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// two-shot: slice q (S wire vectors) is reduced by rank q.  CTA b owns vector range [b*per, (b+1)*per) of EVERY slice,
+// so it only ever depends on what the peers' CTA b wrote (per-CTA barriers suffice).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int kWire>
+__global__ void __launch_bounds__(kCommThreads, 2)
+allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S, float scale, double *sumsq_out) {
+    typedef Wire<kWire> W;
+    constexpr int E = W::kElems;
+    const uint32_t s = comm_begin(c);
+    const int half = s & 1;
+    const size_t per = (S + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = min(S, lo + per);
+
+    // phase 1 (K1): scale + cast my whole bucket into my staging half
+    uint4 *mine = reinterpret_cast<uint4 *>(c.stage(c.rank, half));
+    for (int q = 0; q < c.world; ++q) {
+        for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
+            const size_t g = (size_t)q * S + i;
+            if (g < nvec) {
+                float v[E];
+                load_bucket<E>(bucket, g, n, scale, v);
+                mine[g] = W::pack(v);
+            }
+        }
+    }
+    comm_barrier(c, 0, s);
+
+    // phase 2 (reduce-scatter): I reduce slice `rank` from every peer's staging into my result half
+    uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
+    for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
+        const size_t g = (size_t)c.rank * S + i;
+        if (g < nvec) {
+            uint4 w[DMLB_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+                if (r < c.world) w[r] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.stage(r, half)) + g);
+            float acc[E];
+#pragma unroll
+            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+                if (r < c.world) W::accumulate(acc, w[r]);
+            res[i] = W::pack(acc);
+        }
+    }
+    comm_barrier(c, 1, s);
+
+    // phase 3 (all-gather + K2): pull every rank's reduced slice and widen into the fp32 bucket
+    double part = 0.0;
+    for (int q = 0; q < c.world; ++q) {
+        const uint4 *rq = reinterpret_cast<const uint4 *>(c.result(q, half));
+        for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
+            const size_t g = (size_t)q * S + i;
+            if (g < nvec) {
+                uint4 w = ld_coherent_u4(rq + i);
+                float acc[E];
+#pragma unroll
+                for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+                W::accumulate(acc, w);
+                part += store_bucket<E>(bucket, g, n, acc, sumsq_out != nullptr);
+            }
+        }
+    }
+    if (sumsq_out) {
+        double tot = block_sum(part);
+        if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
+    }
+    comm_end(c, s);
+}
+
+__global__ void __launch_bounds__(kCommThreads) barrier_kernel(const __grid_constant__ CommDev c) {
+    const uint32_t s = comm_begin(c);
+    comm_barrier(c, 0, s);
+    comm_end(c, s);
+}
+
+constexpr size_t kOneshotMaxBytes = 512 * 1024;
+
+}  // namespace dmlb
+
+using namespace dmlb;
+
+extern "C" {
+
+size_t dmlb_comm_arena_bytes(size_t max_message_bytes) {
+    size_t m = (max_message_bytes + 255) & ~(size_t)255;
+    return kHeaderBytes + 4 * m;
+}
+
+int dmlb_comm_create(void **comm, int world, int rank, void *const *arenas, size_t max_message_bytes) {
+    if (!comm || !arenas || world < 1 || world > DMLB_MAX_WORLD || rank < 0 || rank >= world) return DMLB_EINVAL;
+    Comm *c = new (std::nothrow) Comm();
+    if (!c) return DMLB_EINVAL;
+    c->dev.world = world;
+    c->dev.rank = rank;
+    c->dev.msg_cap = (max_message_bytes + 255) & ~(size_t)255;
+    c->dev.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    for (int r = 0; r < DMLB_MAX_WORLD; ++r) c->dev.arena[r] = r < world ? (unsigned char *)arenas[r] : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!c->dev.arena[r] || ((uintptr_t)c->dev.arena[r] & 255)) {
+            delete c;
+            return DMLB_EALIGN;
+        }
+    *comm = c;
+    return DMLB_OK;
+}
+
+int dmlb_comm_destroy(void *comm) {
+    delete reinterpret_cast<Comm *>(comm);
+    return DMLB_OK;
+}
+
+int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float scale, double *sumsq, int algo,
+                        void *stream) {
+    if (!comm || (!bucket && n)) return DMLB_EINVAL;
+    if (wire != DMLB_WIRE_F32 && wire != DMLB_WIRE_BF16) return DMLB_EINVAL;
+    if ((uintptr_t)bucket & 15) return DMLB_EALIGN;
+    if (n == 0) return DMLB_OK;
+    Comm *c = reinterpret_cast<Comm *>(comm);
+    const int E = wire == DMLB_WIRE_BF16 ? 8 : 4;
+    const size_t nvec = (n + E - 1) / E;
+    const size_t bytes = nvec * 16;
+    if (bytes > c->dev.msg_cap) return DMLB_ECAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool oneshot = algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || c->dev.world <= 2));
+    if (oneshot) {
+        size_t want = (nvec + kCommThreads - 1) / kCommThreads;
+        // big one-shot messages (W<=2 takes this path at any size): a few vectors per thread, at most 2 CTAs per SM
+        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
+        if (want > cap) want = cap;
+        int grid = (int)(want < 1 ? 1 : want);
+        if (wire == DMLB_WIRE_BF16)
+            allreduce_oneshot_kernel<DMLB_WIRE_BF16><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);
+        else
+            allreduce_oneshot_kernel<DMLB_WIRE_F32><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);
+    } else {
+        const size_t S = (nvec + c->dev.world - 1) / c->dev.world;
+        size_t want = (S + kCommThreads - 1) / kCommThreads;
+        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
+        if (want > cap) want = cap;
+        int grid = (int)(want < 1 ? 1 : want);
+        if (wire == DMLB_WIRE_BF16)
+            allreduce_twoshot_kernel<DMLB_WIRE_BF16><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, S, scale, sumsq);
+        else
+            allreduce_twoshot_kernel<DMLB_WIRE_F32><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, S, scale, sumsq);
+    }
+    return launched();
+}
+
+int dmlb_comm_barrier(void *comm, void *stream) {
+    if (!comm) return DMLB_EINVAL;
+    Comm *c = reinterpret_cast<Comm *>(comm);
+    barrier_kernel<<<1, kCommThreads, 0, (cudaStream_t)stream>>>(c->dev);
+    return launched();
+}
+
+}  // extern "C"

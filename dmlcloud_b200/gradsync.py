@@ -1,0 +1,257 @@
+"""Gradient-bucket synchronisation: the host side of libdmlb's K1 / K2 / fused peer all-reduce.
+
+The reference enables gradient averaging in exactly one place — `DistributedDataParallel(model, broadcast_buffers=False)`
+at pipeline.py:74 — and the work happens inside torch's C++ Reducer when `loss.backward()` runs (stage.py:282).  The
+drop-in boundary for that path is DDP's communication hook:
+    hook(state, bucket: dist.GradBucket) -> torch.futures.Future[torch.Tensor]
+registered once per DDP instance (torch/nn/parallel/distributed.py:1987).  `GradBucketSync.hook` is that function.
+
+Per bucket it picks one of three routes, all of them running libdmlb kernels on the bucket:
+  peer   (default when a PeerComm could be built and the bucket fits its arena)
+         ONE kernel: scale 1/W + cast -> own staging half -> flag barrier over NVLink peer memory -> rank-ordered fp32
+         sum of all W stagings -> write-back into the fp32 bucket (+ optional sum of squares).  No NCCL.
+  nccl   K1 (scale / scale+cast to bf16) -> torch.distributed all_reduce (NCCL over NVLink) -> K2 (bf16 -> fp32)
+  single W == 1: K1/K2 only (the cast round-trip still happens for the bf16 wire so numerics do not depend on W)
+"""
+import ctypes
+import warnings
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+WIRES = {'fp32': N.WIRE_F32, 'bf16': N.WIRE_BF16}
+
+
+class PeerComm:
+    """A peer-memory communicator: one arena per rank (cudaMalloc'd by libdmlb, exported through CUDA IPC, mapped by all
+    peers).  Drive it from ONE stream at a time.  Gradients and metrics own separate instances."""
+
+    def __init__(self, device, group=None, max_message_bytes=64 << 20):
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > N.MAX_WORLD:
+            raise RuntimeError(f'PeerComm supports up to {N.MAX_WORLD} ranks on one NVSwitch box, got {self.world}')
+        lib = N.cuda_lib(self.device.index)
+        self.max_message_bytes = int(max_message_bytes)
+        self.arena_bytes = int(lib.dmlb_comm_arena_bytes(self.max_message_bytes))
+        self._own = ctypes.c_void_p()
+        N.check(lib.dmlb_malloc(ctypes.byref(self._own), self.arena_bytes), 'malloc(arena)')
+        self._opened = []
+        self.handle = None
+        try:
+            blob = (ctypes.c_ubyte * N.IPC_HANDLE_BYTES)()
+            if self.world > 1:
+                N.check(lib.dmlb_ipc_get_handle(self._own, blob), 'ipc_get_handle')
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(blob), group=group)
+            arenas = (ctypes.c_void_p * self.world)()
+            ok = True
+            for r in range(self.world):
+                if r == self.rank:
+                    arenas[r] = self._own.value
+                    continue
+                p = ctypes.c_void_p()
+                rc = lib.dmlb_ipc_open_handle((ctypes.c_ubyte * N.IPC_HANDLE_BYTES).from_buffer_copy(handles[r]),
+                                              ctypes.byref(p))
+                if rc != N.OK:
+                    ok = False
+                    self._error = N.NativeError(rc, f'ipc_open_handle(rank {r})')
+                    break
+                self._opened.append(p)
+                arenas[r] = p.value
+            votes = [None] * self.world
+            dist.all_gather_object(votes, ok, group=group)
+            if not all(votes):
+                raise RuntimeError(f'peer mapping failed on ranks {[i for i, v in enumerate(votes) if not v]}')
+            comm = ctypes.c_void_p()
+            N.check(lib.dmlb_comm_create(ctypes.byref(comm), self.world, self.rank, arenas, self.max_message_bytes),
+                    'comm_create')
+            self.handle = comm
+            dist.barrier(group=group)  # every arena is mapped (and zero-filled) before anyone launches
+        except Exception:
+            self.close()
+            raise
+
+    @classmethod
+    def try_create(cls, device, group=None, max_message_bytes=64 << 20):
+        """PeerComm or None (with a warning) when CUDA IPC / P2P is unavailable — callers then use the NCCL route.
+        The decision is collective: either every rank gets a communicator or none does."""
+        try:
+            return cls(device, group=group, max_message_bytes=max_message_bytes)
+        except Exception as exc:  # noqa: BLE001 - any failure means "no peer path on this box"
+            warnings.warn(f'peer-memory communicator unavailable ({exc}); using the NCCL route')
+            return None
+
+    def fits(self, wire_bytes):
+        return wire_bytes <= self.max_message_bytes
+
+    def barrier(self, stream=None):
+        N.check(N.cuda_lib(self.device.index).dmlb_comm_barrier(self.handle, N.stream_ptr(stream)), 'comm_barrier')
+
+    def close(self):
+        lib = N.load()
+        if self.handle is not None:
+            lib.dmlb_comm_destroy(self.handle)
+            self.handle = None
+        for p in self._opened:
+            lib.dmlb_ipc_close_handle(p)
+        self._opened = []
+        if self._own is not None and self._own.value:
+            torch.cuda.synchronize(self.device)
+            lib.dmlb_free(self._own)
+            self._own = None
+
+
+class GradBucketSync:
+    """State + hook for `DistributedDataParallel.register_comm_hook` (drop-in for the bucket all-reduce).
+
+    wire:  'fp32' (the reference's numerics; tolerance 1e-6 * max|g|) or 'bf16' (half the NVLink bytes; 1e-2 * max|g|)
+    route: 'auto' | 'peer' | 'nccl'
+    """
+
+    def __init__(self, device, group=None, wire='fp32', route='auto', max_message_bytes=64 << 20, track_sumsq=False):
+        if wire not in WIRES:
+            raise ValueError(f'wire must be one of {list(WIRES)}')
+        if route not in ('auto', 'peer', 'nccl'):
+            raise ValueError("route must be 'auto', 'peer' or 'nccl'")
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('GradBucketSync needs a CUDA device: there is no CPU gradient path in dmlcloud_b200')
+        self.group = group
+        self.wire = wire
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.scale = 1.0 / self.world
+        N.cuda_lib(self.device.index)
+        self.comm = None
+        if self.world > 1 and route in ('auto', 'peer'):
+            self.comm = PeerComm.try_create(self.device, group, max_message_bytes)
+            if self.comm is None and route == 'peer':
+                raise RuntimeError('route="peer" requested but the peer-memory communicator could not be created')
+        self.comm_stream = torch.cuda.Stream(device=self.device)
+        self._staging = {}
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device) if track_sumsq else None
+        self.buckets_seen = 0
+        self.last_routes = {}
+
+    # -- helpers -----------------------------------------------------------------------------------------------------
+    def _stage_for(self, index, n):
+        buf = self._staging.get(index)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            self._staging[index] = buf
+        return buf
+
+    def _done(self, tensor):
+        fut = torch.futures.Future(devices=[self.device])
+        fut.set_result(tensor)
+        return fut
+
+    def zero_sumsq(self):
+        if self.sumsq is not None:
+            self.sumsq.zero_()
+
+    # -- the hook ----------------------------------------------------------------------------------------------------
+    def hook(self, state, bucket):
+        buf = bucket.buffer()
+        return self.reduce_bucket(buf, bucket.index())
+
+    def reduce_bucket(self, buf, index=0):
+        """Average the flat fp32 gradient bucket `buf` across ranks in place; returns a Future of `buf`."""
+        if buf.dtype != torch.float32 or not buf.is_contiguous():
+            raise RuntimeError('GradBucketSync expects contiguous fp32 gradient buckets')
+        lib = N.cuda_lib(self.device.index)  # runs on the autograd thread: per-thread device of libdmlb's runtime
+        n = buf.numel()
+        wire = WIRES[self.wire]
+        wire_bytes = ((n + 7) // 8) * 16 if self.wire == 'bf16' else ((n + 3) // 4) * 16
+        sumsq_ptr = self.sumsq.data_ptr() if self.sumsq is not None else None
+        self.buckets_seen += 1
+
+        if self.world == 1:
+            st = N.stream_ptr()
+            if self.wire == 'bf16':
+                stage = self._stage_for(index, n)
+                N.check(lib.dmlb_bucket_pack_f32_bf16(buf.data_ptr(), stage.data_ptr(), n, self.scale, st), 'pack')
+                N.check(lib.dmlb_bucket_unpack_bf16_f32(stage.data_ptr(), buf.data_ptr(), n, 1.0, sumsq_ptr, st),
+                        'unpack')
+            else:
+                N.check(lib.dmlb_bucket_scale_f32(buf.data_ptr(), n, self.scale, st), 'scale')
+                if sumsq_ptr:
+                    N.check(lib.dmlb_bucket_sumsq_f32(buf.data_ptr(), n, sumsq_ptr, st), 'sumsq')
+            self.last_routes[index] = 'single'
+            return self._done(buf)
+
+        if self.comm is not None and self.comm.fits(wire_bytes) and buf.data_ptr() % 16 == 0:
+            cur = torch.cuda.current_stream(self.device)
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                N.check(lib.dmlb_comm_allreduce(self.comm.handle, buf.data_ptr(), n, wire, self.scale, sumsq_ptr, 0,
+                                                N.stream_ptr(self.comm_stream)), 'comm_allreduce')
+                buf.record_stream(self.comm_stream)
+                fut = self._done(buf)
+            self.last_routes[index] = 'peer'
+            return fut
+
+        # NCCL route: K1 -> all_reduce -> K2
+        self.last_routes[index] = 'nccl'
+        st = N.stream_ptr()
+        if self.wire == 'fp32':
+            N.check(lib.dmlb_bucket_scale_f32(buf.data_ptr(), n, self.scale, st), 'scale')
+            fut = dist.all_reduce(buf, group=self.group, async_op=True).get_future()
+
+            def finish_f32(f):
+                out = f.value()[0]
+                if sumsq_ptr:
+                    N.check(N.cuda_lib(self.device.index).dmlb_bucket_sumsq_f32(out.data_ptr(), n, sumsq_ptr,
+                                                                                 N.stream_ptr()), 'sumsq')
+                return out
+
+            return fut.then(finish_f32)
+
+        stage = self._stage_for(index, n)[:n]
+        N.check(lib.dmlb_bucket_pack_f32_bf16(buf.data_ptr(), stage.data_ptr(), n, self.scale, st), 'pack')
+        fut = dist.all_reduce(stage, group=self.group, async_op=True).get_future()
+
+        def finish_bf16(f):
+            reduced = f.value()[0]
+            N.check(N.cuda_lib(self.device.index).dmlb_bucket_unpack_bf16_f32(
+                reduced.data_ptr(), buf.data_ptr(), n, 1.0, sumsq_ptr, N.stream_ptr()), 'unpack')
+            return buf
+
+        return fut.then(finish_bf16)
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+
+
+def clip_grad_norm_(parameters, max_norm, sumsq=None):
+    """torch.nn.utils.clip_grad_norm_ (reference stage.py:276-279) on libdmlb kernels, without a host sync:
+    sum of squares (fp64 partials) -> coefficient computed on the device -> in-place scale.
+    If `sumsq` (a 1-element fp64 CUDA tensor already holding sum g^2 of exactly these parameters, e.g. accumulated by the
+    fused all-reduce) is given, the first pass is skipped.  Returns the 0-d CUDA tensor holding the total norm."""
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return torch.tensor(0.0)
+    device = grads[0].device
+    lib = N.cuda_lib(device.index)
+    st = N.stream_ptr()
+    if sumsq is None:
+        sumsq = torch.zeros(1, dtype=torch.float64, device=device)
+        for g in grads:
+            N.check(lib.dmlb_bucket_sumsq_f32(_flat_f32(g).data_ptr(), g.numel(), sumsq.data_ptr(), st), 'sumsq')
+    for g in grads:
+        N.check(lib.dmlb_bucket_clip_f32(_flat_f32(g).data_ptr(), g.numel(), sumsq.data_ptr(), float(max_norm), st),
+                'clip')
+    return sumsq.sqrt().to(torch.float32).reshape(())
+
+
+def _flat_f32(g):
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        raise RuntimeError('clip_grad_norm_ (dmlcloud_b200) expects contiguous fp32 gradients')
+    return g

@@ -1,0 +1,898 @@
+"""Metric tracking with a device-resident slab — B200-native replacement of the reference's dmlcloud/metrics.py.
+
+Same public surface (reference file:line in brackets):
+    Reduction [7-21], reduce_tensor [24-41], MetricReducer [44-155], MetricTracker [158-306]
+Same names, argument meaning, return types (CPU tensors in histories) and ValueError conditions.  What changed is where
+the arithmetic happens:
+
+  reference                                               here
+  track(): D2H copy + stream sync per CUDA value [234,72]  one tiny fold launch; the value never leaves the device
+  reduce_locally: torch.stack + mean/sum/amin/amax [107]   running {acc, cnt} cells, updated per step (libdmlb K3)
+  reduce_globally: per metric all_gather_object vote +     ONE kernel per reduce_all(): finalise, exchange all selected
+      all_reduce on gloo [121-141]                          cells over NVLink peer memory, combine in rank order (K4);
+                                                            the vote is the comparison of the count lanes
+
+No CPU path exists for reduced metrics: without CUDA (or without libdmlb.so) tracking a reduced metric raises.
+"""
+import ctypes
+import hashlib
+import struct
+from enum import Enum
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+__all__ = ['Reduction', 'reduce_tensor', 'MetricReducer', 'MetricTracker']
+
+SPLIT_VOTE_MSG = 'Some workers tracked values this epoch and some did not. This is likely a bug.'
+
+
+class Reduction(Enum):
+    MEAN = 'MEAN'
+    SUM = 'SUM'
+    MIN = 'MIN'
+    MAX = 'MAX'
+
+    def as_torch(self):
+        table = {Reduction.SUM: dist.ReduceOp.SUM, Reduction.MIN: dist.ReduceOp.MIN, Reduction.MAX: dist.ReduceOp.MAX}
+        if self not in table:
+            raise ValueError(f'Reduction {self} is not supported by torch')
+        return table[self]
+
+    @property
+    def code(self):
+        return _OP_CODE[self]
+
+
+_OP_CODE = {Reduction.MEAN: N.MEAN, Reduction.SUM: N.SUM, Reduction.MIN: N.MIN, Reduction.MAX: N.MAX}
+_SRC_CODE = {
+    torch.float32: N.F32, torch.float64: N.F64, torch.float16: N.F16, torch.bfloat16: N.BF16,
+    torch.int64: N.I64, torch.int32: N.I32, torch.uint8: N.U8, torch.bool: N.U8,
+}
+
+
+def _is_float(dtype):
+    return dtype.is_floating_point
+
+
+def _result_dtype(dtype, reduction):
+    """dtype of the reduced value, as torch's mean/sum/amin/amax would give it."""
+    if _is_float(dtype):
+        return dtype
+    if reduction is Reduction.MEAN:
+        raise RuntimeError(f'mean(): could not infer output dtype. Input dtype must be either a floating point or '
+                           f'complex dtype. Got: {str(dtype).replace("torch.", "").capitalize()}')
+    if reduction is Reduction.SUM:
+        return torch.int64
+    return dtype
+
+
+def _normalize_dims(dim, ndim):
+    if dim is None:
+        return list(range(ndim))
+    dims = [dim] if isinstance(dim, int) else list(dim)
+    out = []
+    for d in dims:
+        if d < -ndim or d >= max(ndim, 1):
+            raise IndexError(f'Dimension out of range (expected to be in range of [{-ndim}, {ndim - 1}], but got {d})')
+        out.append(d % ndim if ndim else 0)
+    if len(set(out)) != len(out):
+        raise RuntimeError('dim appears multiple times in the list of dims')
+    return out
+
+
+def _lanes_k(shape, dims):
+    """Split a value shape into (residual shape, #cells, #elements folded per cell) for reduced dims `dims`."""
+    residual = [s for i, s in enumerate(shape) if i not in dims]
+    lanes = 1
+    for s in residual:
+        lanes *= s
+    k = 1
+    for i in dims:
+        k *= shape[i]
+    return residual, lanes, k
+
+
+def _arrange(value, dims):
+    """Return `value` laid out [lanes, k] row-major (reduced dims trailing).  A view when possible, else one copy."""
+    nd = value.dim()
+    keep = [i for i in range(nd) if i not in dims]
+    order = keep + sorted(dims)
+    if order != list(range(nd)):
+        value = value.permute(order)
+    return value.contiguous()
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# device slab
+# ----------------------------------------------------------------------------------------------------------------------
+class _PendingResult:
+    """Results of one reduce launch on their way to the host (async D2H + event)."""
+
+    def __init__(self, slab, host, event, capacity):
+        self.slab, self.host, self.event, self.capacity = slab, host, event, capacity
+        self._parsed = None
+
+    def ready(self):
+        return self.event.query()
+
+    def get(self):
+        if self._parsed is None:
+            self.event.synchronize()
+            cap = self.capacity
+            status = int(self.host[:4].view(torch.int32)[0])
+            vals = self.host[8:8 + 8 * cap].view(torch.int64).clone()
+            flags = self.host[8 + 8 * cap:8 + 9 * cap].clone()
+            self.slab._release_host(self.host)
+            self.host = None
+            self._parsed = (status, vals, flags)
+        return self._parsed
+
+
+class DeviceSlab:
+    """HBM layout: acc u64[C] | cnt i64[C] | desc u32[C]  +  out = status(8 B) | val u64[C] | flag u8[C].
+    One instance per tracker; every launch goes on the caller's current stream."""
+
+    GROW = 1024
+
+    def __init__(self, device=None, comm=None, group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('dmlcloud_b200 reduces metrics on a CUDA device only (no CPU fallback) and no CUDA '
+                               'device is available')
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('dmlcloud_b200 metric slab needs a CUDA device (no CPU fallback)')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.lib = N.cuda_lib(self.device.index)
+        self.comm = comm  # gradsync.PeerComm (fused NVLink exchange) or None (torch.distributed all_gather exchange)
+        self.group = group
+        self.capacity = 0
+        self.n_cells = 0
+        self.acc = self.cnt = self.desc = self.out = None
+        self._host_pool = []
+        self._imm = []
+        self._imm_cells = set()
+        self._grow(self.GROW)
+
+    # -- memory ------------------------------------------------------------------------------------------------------
+    def _grow(self, capacity):
+        new = {
+            'acc': torch.zeros(capacity, dtype=torch.int64, device=self.device),
+            'cnt': torch.zeros(capacity, dtype=torch.int64, device=self.device),
+            'desc': torch.zeros(capacity, dtype=torch.int32, device=self.device),
+        }
+        if self.capacity:
+            for k, t in new.items():
+                t[:self.capacity].copy_(getattr(self, k))
+        self.acc, self.cnt, self.desc = new['acc'], new['cnt'], new['desc']
+        self.out = torch.zeros(8 + 9 * capacity, dtype=torch.uint8, device=self.device)
+        self.capacity = capacity
+        self._host_pool = []
+
+    def _lib(self):
+        return N.cuda_lib(self.device.index)
+
+    def alloc(self, lanes, desc_word):
+        if self.n_cells + lanes > self.capacity:
+            self.flush()
+            self._grow(max(self.capacity * 2, self.n_cells + lanes))
+        c0 = self.n_cells
+        self.n_cells += lanes
+        self.desc[c0:c0 + lanes] = desc_word
+        N.check(self._lib().dmlb_metric_reset(self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), c0,
+                                              c0 + lanes, N.stream_ptr()), 'metric_reset')
+        return c0
+
+    def reset_cells(self, cell, lanes):
+        self.flush()
+        N.check(self._lib().dmlb_metric_reset(self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), cell,
+                                              cell + lanes, N.stream_ptr()), 'metric_reset')
+
+    def release_to(self, n_cells):
+        """Stack-style free (scratch users)."""
+        self.flush()
+        self.n_cells = n_cells
+
+    def _acquire_host(self):
+        size = 8 + 9 * self.capacity
+        while self._host_pool:
+            h = self._host_pool.pop()
+            if h.numel() == size:
+                return h
+        return torch.empty(size, dtype=torch.uint8, pin_memory=True)
+
+    def _release_host(self, host):
+        if host.numel() == 8 + 9 * self.capacity and len(self._host_pool) < 16:
+            self._host_pool.append(host)
+
+    # -- fold --------------------------------------------------------------------------------------------------------
+    def fold_imm(self, cell, value, is_int):
+        """Queue a host scalar; it rides along with the next launch (or the reduce)."""
+        if cell in self._imm_cells or len(self._imm) >= N.MAX_FOLD_ENTRIES - 1:
+            self.flush()
+        bits = int(value) if is_int else struct.unpack('<q', struct.pack('<d', float(value)))[0]
+        self._imm.append(N.FoldEntry(None, bits, N.F64, cell, 1, 1, 1, 0))
+        self._imm_cells.add(cell)
+
+    def fold_device(self, cell, lanes, k, tensor, steps=1):
+        """tensor: contiguous CUDA tensor laid out [steps, lanes, k]."""
+        code = _SRC_CODE.get(tensor.dtype)
+        if code is None:
+            tensor = tensor.to(torch.float64 if tensor.dtype.is_floating_point else torch.int64)
+            code = _SRC_CODE[tensor.dtype]
+        if any(cell <= c < cell + lanes for c in self._imm_cells):
+            self.flush()
+        entries = self._imm + [N.FoldEntry(tensor.data_ptr(), 0, code, cell, lanes, k, steps, 0)]
+        self._imm, self._imm_cells = [], set()
+        self._launch_fold(entries)
+        return tensor  # caller keeps it alive until the stream passes (torch's allocator is stream-ordered)
+
+    def flush(self):
+        if self._imm:
+            entries, self._imm, self._imm_cells = self._imm, [], set()
+            self._launch_fold(entries)
+
+    def _launch_fold(self, entries):
+        arr = (N.FoldEntry * len(entries))(*entries)
+        N.check(self._lib().dmlb_metric_fold(self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), arr,
+                                             len(entries), N.stream_ptr()), 'metric_fold')
+
+    # -- reduce ------------------------------------------------------------------------------------------------------
+    def reduce(self, global_ranges, local_ranges, layout_hash, reset=True, exchange=True, to_host=True):
+        """Finalise + cross-rank combine.  `global_ranges` are the cells of globally-reduced metrics (identical layout
+        on every rank, covered by `layout_hash`, exchanged); `local_ranges` are rank-local metrics (never exchanged,
+        may differ between ranks).  Returns a _PendingResult (to_host) or None."""
+        self.flush()
+        lib = self._lib()
+        world, rank = _world(self.group)
+        if not exchange:
+            world = 1
+        st = N.stream_ptr()
+        out = self.out
+        status_ptr = out.data_ptr()
+        val_ptr = out.data_ptr() + 8
+        flag_ptr = out.data_ptr() + 8 + 8 * self.capacity
+        N.check(lib.dmlb_memset_async(status_ptr, 0, 8, st), 'memset')
+
+        def launch(comm_handle, ranges):
+            # > DMLB_MAX_RANGES fragments (pathological prefix selections) take several launches
+            chunks = [ranges[i:i + N.MAX_RANGES] for i in range(0, len(ranges), N.MAX_RANGES)] or [[]]
+            for chunk in chunks:
+                if not chunk and comm_handle is None:
+                    continue
+                arr = (N.Range * max(len(chunk), 1))(*[N.Range(b, e) for b, e in chunk])
+                N.check(lib.dmlb_metric_reduce(comm_handle, self.acc.data_ptr(), self.cnt.data_ptr(),
+                                               self.desc.data_ptr(), self.n_cells, arr, len(chunk), layout_hash,
+                                               int(reset), val_ptr, flag_ptr, status_ptr, st), 'metric_reduce')
+
+        if world == 1:
+            launch(None, list(global_ranges) + list(local_ranges))
+        elif self.comm is not None:
+            # fused path: global cells first (their record index must agree across ranks), rank-local cells after
+            launch(self.comm.handle, list(global_ranges) + list(local_ranges))
+        else:
+            if local_ranges:
+                launch(None, list(local_ranges))
+            self._reduce_via_collective(lib, list(global_ranges), layout_hash, reset, world, rank, val_ptr, flag_ptr,
+                                        status_ptr, st)
+        if not to_host:
+            return None
+        host = self._acquire_host()
+        host.copy_(out, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        return _PendingResult(self, host, event, self.capacity)
+
+    def _reduce_via_collective(self, lib, ranges, layout_hash, reset, world, rank, val_ptr, flag_ptr, status_ptr, st):
+        """Exchange through torch.distributed (NCCL all_gather of the packed record) when no peer arena is attached.
+        Record sizes must agree before a tensor collective can be issued, so the layout is voted on first."""
+        n_sel = sum(e - b for b, e in ranges)
+        votes = [None] * world
+        dist.all_gather_object(votes, (layout_hash, n_sel), group=self.group)
+        if any(v != votes[0] for v in votes):
+            raise ValueError(SPLIT_VOTE_MSG)
+        if n_sel == 0:
+            return
+        if len(ranges) > N.MAX_RANGES:
+            raise RuntimeError(f'metric selection is fragmented into {len(ranges)} cell ranges (max {N.MAX_RANGES})')
+        arr = (N.Range * len(ranges))(*[N.Range(b, e) for b, e in ranges])
+        words = int(lib.dmlb_metric_record_words(n_sel))
+        record = torch.empty(words, dtype=torch.int64, device=self.device)
+        N.check(lib.dmlb_metric_finalize(self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), arr,
+                                         len(ranges), layout_hash, int(reset), record.data_ptr(), st),
+                'metric_finalize')
+        gathered = torch.empty(world * words, dtype=torch.int64, device=self.device)
+        backend = dist.get_backend(self.group)
+        if 'nccl' in str(backend):
+            dist.all_gather_into_tensor(gathered, record, group=self.group)
+        else:  # a gloo-only process group cannot move CUDA tensors: bounce the (tiny) record through the host
+            cpu = [torch.empty(words, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(cpu, record.cpu(), group=self.group)
+            gathered.copy_(torch.cat(cpu))
+        N.check(lib.dmlb_metric_combine(gathered.data_ptr(), world, rank, self.desc.data_ptr(), arr, len(ranges),
+                                        val_ptr, flag_ptr, status_ptr, N.stream_ptr()), 'metric_combine')
+        self._keep = (record, gathered)
+
+    def result_view(self, cell, lanes, is_int):
+        """Device view of the last reduce's values for cells [cell, cell+lanes) (no host sync)."""
+        vals = self.out[8:8 + 8 * self.capacity].view(torch.int64 if is_int else torch.float64)
+        return vals[cell:cell + lanes]
+
+    # -- checkpoint --------------------------------------------------------------------------------------------------
+    def export_cells(self, cell, lanes):
+        self.flush()
+        return self.acc[cell:cell + lanes].cpu(), self.cnt[cell:cell + lanes].cpu()
+
+    def import_cells(self, cell, acc, cnt):
+        self.acc[cell:cell + acc.numel()].copy_(acc)
+        self.cnt[cell:cell + cnt.numel()].copy_(cnt)
+
+
+_scratch = {}
+
+
+def _scratch_slab(device):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('dmlcloud_b200 reduces on the GPU only: the tensor must live on a CUDA device '
+                           '(no CPU fallback)')
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _scratch:
+        _scratch[idx] = DeviceSlab(torch.device('cuda', idx))
+    return _scratch[idx]
+
+
+def _desc_word(reduction, dtype, globally):
+    is_int = not _is_float(dtype)
+    f64 = dtype == torch.float64
+    return reduction.code | (int(is_int) << 2) | (int(bool(globally)) << 3) | (int(f64) << 4)
+
+
+def _layout_hash(items):
+    h = hashlib.blake2b(repr(items).encode(), digest_size=8).digest()
+    return int.from_bytes(h, 'little')
+
+
+def _device_reduce(stacked, reduction, dims, steps_axis, group=None, globally=False):
+    """Reduce a CUDA tensor over `dims` (and the leading stack axis when steps_axis) with the slab kernels.
+    Returns (device tensor | None, status tensor view) without any host sync."""
+    dtype = stacked.dtype
+    out_dtype = _result_dtype(dtype, reduction)
+    slab = _scratch_slab(stacked.device)
+    if steps_axis:
+        steps = stacked.shape[0]
+        value_shape = list(stacked.shape[1:])
+    else:
+        steps = 1
+        value_shape = list(stacked.shape)
+    residual, lanes, k = _lanes_k(value_shape, dims)
+    nd = len(value_shape)
+    keep = [i for i in range(nd) if i not in dims]
+    order = keep + sorted(dims)
+    if order != list(range(nd)):
+        perm = ([0] + [o + 1 for o in order]) if steps_axis else order
+        stacked = stacked.permute(perm)
+    stacked = stacked.contiguous()
+    mark = slab.n_cells
+    cell = slab.alloc(lanes, _desc_word(reduction, dtype, globally))
+    if stacked.numel():
+        slab.fold_device(cell, lanes, k, stacked, steps=steps)
+    slab.group = group
+    layout = _layout_hash(('reduce', lanes, reduction.value, str(dtype)))
+    rng = [(cell, cell + lanes)]
+    slab.reduce(rng if globally else [], [] if globally else rng, layout, reset=True, exchange=globally, to_host=False)
+    is_int = not _is_float(dtype)
+    result = slab.result_view(cell, lanes, is_int).to(out_dtype).reshape(residual)
+    status = slab.out[:4].view(torch.int32)
+    slab.release_to(mark)
+    return result, status
+
+
+def reduce_tensor(tensor, reduction, dim=None):
+    """Local reduction of a CUDA tensor over `dim` (all dims when None) — reference metrics.py:24-41."""
+    if not isinstance(tensor, torch.Tensor):
+        raise ValueError('tensor must be a torch.Tensor')
+    if not isinstance(reduction, Reduction):
+        raise ValueError(f'Unknown reduction {reduction}')
+    dims = _normalize_dims(dim, tensor.dim())
+    result, _ = _device_reduce(tensor.detach(), reduction, dims, steps_axis=False)
+    return result
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MetricReducer — standalone, list semantics kept (reference metrics.py:44-155)
+# ----------------------------------------------------------------------------------------------------------------------
+class MetricReducer:
+    """Stores per-step values and reduces them at the end of an epoch (reference metrics.py:44-155).
+
+    The value list is kept (on the device the values live on — no D2H, no sync) because the reference lets callers
+    index, replace and delete entries and even change `reduction` between reduces.  The reduction itself is one fold
+    launch over the stacked values plus one finalise/exchange launch of libdmlb.  `MetricTracker` does not use this
+    list-backed class on its hot path: it folds every value into its slab as it is tracked.
+    """
+
+    def __init__(self, reduction=Reduction.MEAN, dim=None, globally=True):
+        if reduction not in [Reduction.MEAN, Reduction.SUM, Reduction.MIN, Reduction.MAX]:
+            raise ValueError(f'Unknown reduction {reduction}')
+        self.values = []
+        self.reduction = reduction
+        self.globally = globally
+        if isinstance(dim, int):
+            self.dim = [dim]
+        elif dim is not None:
+            self.dim = list(dim)
+        else:
+            self.dim = None
+
+    @staticmethod
+    def _snapshot(value):
+        value = torch.as_tensor(value)
+        return value.detach().clone() if value.is_cuda else value.detach()
+
+    def append(self, value):
+        self.values.append(self._snapshot(value))
+
+    def extend(self, values):
+        for value in values:
+            self.append(value)
+
+    def __iadd__(self, value):
+        self.append(value)
+        return self
+
+    def __setitem__(self, idx, value):
+        self.values[idx] = self._snapshot(value)
+
+    def __getitem__(self, idx):
+        return self.values[idx]
+
+    def __delitem__(self, idx):
+        del self.values[idx]
+
+    def __len__(self):
+        return len(self.values)
+
+    def __iter__(self):
+        return iter(self.values)
+
+    def clear(self):
+        self.values.clear()
+
+    def reduce_and_append(self, value):
+        self.values.append(reduce_tensor(_to_cuda(torch.as_tensor(value)), self.reduction, dim=self.dim))
+
+    def _stacked(self):
+        return torch.stack([_to_cuda(v) for v in self.values])
+
+    def reduce_locally(self):
+        if len(self.values) == 0:
+            return None
+        stacked = self._stacked()
+        dims = _normalize_dims(self.dim, stacked.dim() - 1)
+        result, _ = _device_reduce(stacked, self.reduction, dims, steps_axis=True)
+        return result
+
+    def reduce_globally(self, group=None):
+        world, _ = _world(group)
+        if not self.globally or world == 1:
+            return self.reduce_locally()
+        # The emptiness vote travels with the values (count lanes); an empty rank still has to take part.
+        if len(self.values) == 0:
+            # shape unknown on this rank: vote through the layout header (lanes=0) and let the others decide
+            votes = [None] * world
+            dist.all_gather_object(votes, ('empty',), group=group)
+            if all(v == ('empty',) for v in votes):
+                return None
+            raise ValueError(SPLIT_VOTE_MSG)
+        stacked = self._stacked()
+        dims = _normalize_dims(self.dim, stacked.dim() - 1)
+        votes = [None] * world
+        dist.all_gather_object(votes, ('values',), group=group)
+        if any(v != ('values',) for v in votes):
+            raise ValueError(SPLIT_VOTE_MSG)
+        result, status = _device_reduce(stacked, self.reduction, dims, steps_axis=True, group=group, globally=True)
+        if int(status[0]) != N.METRIC_OK:
+            raise ValueError(SPLIT_VOTE_MSG)
+        return result
+
+    def state_dict(self):
+        return {'reduction': self.reduction, 'dim': self.dim, 'globally': self.globally, 'values': self.values}
+
+    def load_state_dict(self, state):
+        self.reduction = state['reduction']
+        self.dim = state['dim']
+        self.globally = state['globally']
+        self.values = state['values']
+
+
+def _to_cuda(t):
+    if t.is_cuda:
+        return t
+    if not torch.cuda.is_available():
+        raise RuntimeError('dmlcloud_b200 reduces metrics on the GPU only (no CPU fallback) and no CUDA device is '
+                           'available')
+    return t.to(torch.device('cuda', torch.cuda.current_device()))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# slab-backed reducer used by MetricTracker
+# ----------------------------------------------------------------------------------------------------------------------
+class SlabMetric:
+    """What `tracker.reducers[name]` holds: the reference MetricReducer's append/len/clear/state_dict face over a run
+    of slab cells.  Values are folded on arrival and not retained."""
+
+    def __init__(self, tracker, name, reduction=Reduction.MEAN, dim=None, globally=True):
+        if reduction not in [Reduction.MEAN, Reduction.SUM, Reduction.MIN, Reduction.MAX]:
+            raise ValueError(f'Unknown reduction {reduction}')
+        self._tracker = tracker
+        self.name = name
+        self.reduction = reduction
+        self.globally = globally
+        if isinstance(dim, int):
+            self.dim = [dim]
+        elif dim is not None:
+            self.dim = list(dim)
+        else:
+            self.dim = None
+        self.cell = None  # first slab cell; allocated when the first value shows its shape / dtype
+        self.lanes = 0
+        self.k = 0
+        self.value_shape = None
+        self.residual_shape = None
+        self.dtype = None
+        self.count = 0  # values appended since the last reduce (host-side mirror of the count lanes)
+        self._keepalive = None
+
+    # shape / dtype discovery on the first value
+    def _bind(self, shape, dtype):
+        _result_dtype(dtype, self.reduction)  # raises for MEAN on integer values, like torch.mean would at reduce time
+        dims = _normalize_dims(self.dim, len(shape))
+        self.value_shape = list(shape)
+        self.residual_shape, self.lanes, self.k = _lanes_k(self.value_shape, dims)
+        self._dims = dims
+        self.dtype = dtype
+        slab = self._tracker._slab_or_create()
+        self.cell = slab.alloc(self.lanes, _desc_word(self.reduction, dtype, self.globally))
+
+    @property
+    def is_int(self):
+        return not _is_float(self.dtype)
+
+    def append(self, value):
+        slab = self._tracker._slab_or_create()
+        if isinstance(value, torch.Tensor):
+            value = value.detach()
+            if value.dim() == 0 and not value.is_cuda:
+                dtype, scalar = value.dtype, value.item()
+            else:
+                dtype, scalar = value.dtype, None
+        elif isinstance(value, bool):
+            dtype, scalar = torch.bool, int(value)
+        elif isinstance(value, int):
+            dtype, scalar = torch.int64, value
+        elif isinstance(value, float):
+            dtype, scalar = torch.float32, value
+        else:
+            value = torch.as_tensor(value)
+            return self.append(value)
+        shape = [] if scalar is not None else list(value.shape)
+        if self.cell is None:
+            self._bind(shape, dtype)
+        elif shape != self.value_shape:
+            raise RuntimeError(f'stack expects each tensor to be equal size, but got {self.value_shape} and {shape} '
+                               f'for metric {self.name}')
+        if scalar is not None:
+            slab.fold_imm(self.cell, scalar, self.is_int)
+        else:
+            if not value.is_cuda:
+                value = value.to(slab.device)
+            arranged = _arrange(value, self._dims) if value.dim() else value.reshape(1)
+            self._keepalive = slab.fold_device(self.cell, self.lanes, self.k, arranged)
+        self.count += 1
+
+    def extend(self, values):
+        for value in values:
+            self.append(value)
+
+    def __iadd__(self, value):
+        self.append(value)
+        return self
+
+    def __len__(self):
+        return self.count
+
+    def clear(self):
+        if self.cell is not None and self.count:
+            self._tracker._slab_or_create().reset_cells(self.cell, self.lanes)
+        self.count = 0
+
+    def layout_item(self):
+        return (self.name, self.lanes, self.reduction.value, str(self.dtype), bool(self.globally))
+
+    def state_dict(self):
+        state = {'reduction': self.reduction, 'dim': self.dim, 'globally': self.globally, 'values': [],
+                 'count': self.count, 'partial': None}
+        if self.cell is not None:
+            acc, cnt = self._tracker._slab_or_create().export_cells(self.cell, self.lanes)
+            state['partial'] = {'acc': acc, 'cnt': cnt, 'shape': self.value_shape, 'dtype': self.dtype}
+        return state
+
+    def load_state_dict(self, state):
+        self.reduction = state['reduction']
+        self.dim = state['dim']
+        self.globally = state['globally']
+        self.count = state.get('count', 0)
+        partial = state.get('partial')
+        if partial is not None:
+            self.cell = None
+            self._bind(partial['shape'], partial['dtype'])
+            self._tracker._slab_or_create().import_cells(self.cell, partial['acc'], partial['cnt'])
+        for value in state.get('values', []):  # a reference-format checkpoint: replay its retained values
+            self.append(value)
+
+
+class _Deferred:
+    """History placeholder for a reduce whose result has not been brought to the host yet."""
+    __slots__ = ('pending', 'metric')
+
+    def __init__(self, pending, metric):
+        self.pending, self.metric = pending, metric
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MetricTracker (reference metrics.py:158-306)
+# ----------------------------------------------------------------------------------------------------------------------
+class MetricTracker:
+    """Keeps track of multiple metrics and their per-epoch history (reference metrics.py:158-306).
+
+    Extensions over the reference (all optional):
+      bind(device, comm, group)   attach the CUDA device / peer communicator / process group (the pipeline does this)
+      deferred = True             reduce_all() does not wait for the results: histories are materialised (one event
+                                  sync) on first access — lets the exchange run every step without a host round trip
+      reduce_live(prefix)         per-step cross-rank view of the running values, without closing the epoch
+    """
+
+    def __init__(self):
+        self._histories = {}
+        self.reducers = {}
+        self.epoch = 1
+        self.deferred = False
+        self._slab = None
+        self._device = None
+        self._comm = None
+        self._group = None
+        self._has_deferred = False
+
+    # -- wiring ------------------------------------------------------------------------------------------------------
+    def bind(self, device=None, comm=None, group=None, slab=None):
+        self._device, self._comm, self._group = device, comm, group
+        if slab is not None:
+            self._slab = slab
+        elif self._slab is not None:
+            self._slab.comm, self._slab.group = comm, group
+
+    def _slab_or_create(self):
+        if self._slab is None:
+            self._slab = DeviceSlab(self._device, comm=self._comm, group=self._group)
+        return self._slab
+
+    @property
+    def histories(self):
+        self._materialize()
+        return self._histories
+
+    @histories.setter
+    def histories(self, value):
+        self._histories = value
+
+    def _materialize(self):
+        if not self._has_deferred:
+            return
+        self._has_deferred = False
+        for history in self._histories.values():
+            for i, entry in enumerate(history):
+                if isinstance(entry, _Deferred):
+                    history[i] = self._decode(entry.pending, entry.metric)
+
+    @staticmethod
+    def _decode(pending, metric):
+        status, vals, flags = pending.get()
+        if status != N.METRIC_OK:
+            raise ValueError(SPLIT_VOTE_MSG)
+        if isinstance(metric, _VoteOnly):
+            return None
+        c0, lanes = metric.cell, metric.lanes
+        if int(flags[c0]) == 1:
+            return None
+        out_dtype = _result_dtype(metric.dtype, metric.reduction)
+        raw = vals[c0:c0 + lanes]
+        if not metric.is_int:
+            raw = raw.view(torch.float64)
+        return raw.to(out_dtype).reshape(metric.residual_shape)
+
+    # -- dict protocol (reference 176-193) ---------------------------------------------------------------------------
+    def __getitem__(self, name):
+        if name not in self:
+            raise ValueError(f'Metric {name} does not exist')
+        return list(self.histories[name])[: self.epoch - 1]
+
+    def __contains__(self, name):
+        return name in self._histories
+
+    def __len__(self):
+        return len(self._histories)
+
+    def __iter__(self):
+        return iter(self._histories)
+
+    def current_value(self, name):
+        if name not in self:
+            raise ValueError(f'Metric {name} does not exist')
+        if self.has_value(name):
+            return self.histories[name][-1]
+        return None
+
+    def is_reduced_metric(self, name):
+        if name not in self:
+            raise ValueError(f'Metric {name} does not exist')
+        return name in self.reducers
+
+    def has_value(self, name):
+        if name not in self:
+            raise ValueError(f'Metric {name} does not exist')
+        return len(self._histories[name]) >= self.epoch
+
+    def register_metric(self, name, reduction=None, dim=None, globally=True):
+        if name in self:
+            raise ValueError(f'Metric {name} already exists')
+        if dim is not None and reduction is None:
+            raise ValueError('If dim is specified, reduction must be specified as well')
+        self._histories[name] = [None] * (self.epoch - 1)
+        if reduction is not None:
+            self.reducers[name] = SlabMetric(self, name, reduction=reduction, dim=dim, globally=globally)
+
+    def track(self, name, value):
+        if name not in self:
+            raise ValueError(f'Metric {name} does not exist')
+        if self.has_value(name):
+            raise ValueError(f'History for {name} already has a value for epoch {self.epoch}')
+        reducer = self.reducers.get(name)
+        if reducer is not None:
+            reducer.append(value)  # folded on the device, no D2H (reference: metrics.py:234 + 72 copy and sync)
+        else:
+            if isinstance(value, torch.Tensor):
+                value = value.detach().to('cpu', non_blocking=True)
+            self._histories[name].append(value)
+
+    # -- reduce ------------------------------------------------------------------------------------------------------
+    def _select(self, prefix, strict):
+        """Metrics a reduce_all(prefix, strict) call covers, in registration order (reference 258-266)."""
+        plain, reduced = [], []
+        for name in self._histories:
+            if prefix is not None and not name.startswith(prefix):
+                continue
+            if self.has_value(name):
+                if strict:
+                    raise ValueError(f'History for {name} has already been reduced for epoch {self.epoch}')
+                continue
+            reducer = self.reducers.get(name)
+            (plain if reducer is None else reduced).append(name)
+        return plain, reduced
+
+    @staticmethod
+    def _ranges(metrics):
+        ranges = []
+        for m in metrics:
+            if ranges and ranges[-1][1] == m.cell:
+                ranges[-1][1] = m.cell + m.lanes
+            else:
+                ranges.append([m.cell, m.cell + m.lanes])
+        return [tuple(r) for r in ranges]
+
+    def _launch(self, bound, reset):
+        """One reduce launch for the bound (cell-owning) metrics.  Globally-reduced metrics go first and define the
+        cross-rank layout; rank-local metrics (globally=False) follow and are never exchanged."""
+        slab = self._slab_or_create()
+        glob = [m for m in bound if m.globally]
+        loc = [m for m in bound if not m.globally]
+        layout = _layout_hash([m.layout_item() for m in glob])
+        return slab.reduce(self._ranges(glob), self._ranges(loc), layout, reset=reset, exchange=True)
+
+    def reduce_all(self, prefix=None, strict=True):
+        """Reduces all metrics and appends their reduced values to the history (reference metrics.py:249-273).
+        One kernel launch + one small D2H copy for ALL selected metrics, instead of three collectives per metric."""
+        plain, reduced = self._select(prefix, strict)
+        for name in plain:
+            self._histories[name].append(None)
+        if not reduced:
+            return
+        metrics = [self.reducers[name] for name in reduced]
+        bound = [m for m in metrics if m.cell is not None]
+        world, _ = _world(self._group)
+        pending = None
+        # With W>1 every rank that selected a globally-reduced metric takes part in the exchange, even if it has
+        # nothing to contribute: that is how "some workers tracked values and some did not" (reference 124-128) shows.
+        if bound or (world > 1 and any(m.globally for m in metrics)):
+            pending = self._launch(bound, reset=True)
+        vote_carrier = None
+        for m in metrics:
+            if m.cell is None:
+                self._histories[m.name].append(None)
+                if vote_carrier is None and m.globally:
+                    vote_carrier = m
+            else:
+                self._histories[m.name].append(_Deferred(pending, m))
+                self._has_deferred = True
+            m.count = 0
+        if pending is not None and vote_carrier is not None:
+            self._histories[vote_carrier.name][-1] = _Deferred(pending, _VoteOnly())
+            self._has_deferred = True
+        if not self.deferred:
+            self._materialize()
+
+    def reduce_live(self, prefix=None):
+        """Cross-rank view of the running values of all (prefix-matching) reduced metrics, WITHOUT closing the epoch:
+        the per-step metric exchange of BASELINE configs 2/3.  Returns {name: handle}; `handle.value()` brings the
+        number to the host (one event sync) when it is actually needed."""
+        metrics = [m for name, m in self.reducers.items()
+                   if (prefix is None or name.startswith(prefix)) and m.cell is not None and not self.has_value(name)]
+        if not metrics:
+            return {}
+        pending = self._launch(metrics, reset=False)
+        return {m.name: _Live(pending, m) for m in metrics}
+
+    def next_epoch(self):
+        """Reduces all metrics (if not already reduced) and advances the epoch counter (reference 275-280)."""
+        self.reduce_all(strict=False)
+        self.epoch += 1
+
+    # -- checkpoint (reference 282-296) ------------------------------------------------------------------------------
+    def state_dict(self):
+        return {
+            'epoch': self.epoch,
+            'histories': dict(self.histories),
+            'reducers': {name: reducer.state_dict() for name, reducer in self.reducers.items()},
+        }
+
+    def load_state_dict(self, state):
+        self.epoch = state['epoch']
+        self._histories = state['histories']
+        self.reducers = {}
+        for name, reducer_state in state['reducers'].items():
+            metric = SlabMetric(self, name)
+            metric.load_state_dict(reducer_state)
+            self.reducers[name] = metric
+
+    def __str__(self):
+        s = 'MetricTracker('
+        for name, history in self.histories.items():
+            s += f'\n  {name}: {history}'
+        if len(self._histories) > 0:
+            s += '\n)'
+        else:
+            s += ')'
+        return s
+
+
+class _VoteOnly:
+    """Stand-in metric for a reduce that only carried the emptiness vote (this rank had no cells)."""
+    cell, lanes, dtype, reduction, residual_shape, is_int = 0, 0, torch.float32, Reduction.SUM, [], False
+
+
+class _Live:
+    def __init__(self, pending, metric):
+        self.pending, self.metric = pending, metric
+
+    def value(self):
+        return MetricTracker._decode(self.pending, self.metric)

@@ -1,0 +1,472 @@
+"""Host-side logic of the product on a CPU-only box.
+
+The arithmetic engine is replaced — by the TESTS, through `MetricTracker.bind(slab=...)` — with oracle/slab_oracle.py, so
+what is exercised here is the Python host code the GPU path shares: registration / back-fill / strict / prefix / vote
+logic, selection ordering, deferred materialisation, state round-trips, the Stage loop, sharding, checkpoint dirs and
+the process-group helpers, including world_size-2 gloo runs.  The product itself has no such engine: without CUDA it
+raises (tests/test_abi.py::test_product_refuses_to_compute_without_cuda).
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_json
+from helpers import assert_histories_match, init_gloo, replay_metric_script, spawn
+from oracle.slab_oracle import OracleSlab
+
+
+def make_tracker(group=None):
+    from dmlcloud_b200.metrics import MetricTracker
+
+    t = MetricTracker()
+    t.bind(slab=OracleSlab(group))
+    return t
+
+
+# --------------------------------------------------------------------------------------------------- tracker semantics
+class TestTrackerHostLogic:
+    def test_reference_tracker_unit_tests(self):
+        # mirrors reference test/test_metrics.py:92-204 on the product's MetricTracker
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        assert len(t) == 0
+        t.register_metric('A')
+        t.register_metric('B', reduction=Reduction.MEAN, globally=False)
+        assert len(t) == 2 and 'A' in t and 'B' in t and 'C' not in t
+        assert isinstance(t['A'], list) and len(t['A']) == 0
+        assert not t.is_reduced_metric('A') and t.is_reduced_metric('B')
+
+        t = make_tracker()
+        t.register_metric('A')
+        t.next_epoch()
+        assert len(t['A']) == 1 and t['A'][0] is None and t.epoch == 2
+        t.next_epoch()
+        assert len(t['A']) == 2 and t['A'][1] is None and t.epoch == 3
+        t.register_metric('B', reduction=Reduction.MEAN, globally=False)
+        assert len(t['B']) == 2 and t['B'][1] is None
+
+    def test_track_and_double_track(self):
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        t.register_metric('A')
+        t.track('A', 1)
+        with pytest.raises(ValueError):
+            t.track('A', 42)
+        t.next_epoch()
+        t.track('A', 42)
+        t.register_metric('B', reduction=Reduction.MEAN, globally=False)
+        for v in (2.0, 4.0, 1.0, 1.0):
+            t.track('B', v)
+        t.next_epoch()
+        assert t['A'] == [1, 42]
+        assert t['B'] == [None, torch.tensor(2.0)]
+        assert t['B'][1].dtype == torch.float32
+        str(t)
+
+    def test_manual_reduction_prefix_strict(self):
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        t.register_metric('A')
+        t.register_metric('B', reduction=Reduction.SUM, globally=False)
+        for v in (1.0, 2.0, 3.0):
+            t.track('B', v)
+        t.reduce_all(prefix='B')
+        assert t.has_value('B') and not t.has_value('A')
+        assert t.current_value('B').item() == 6.0 and t.current_value('A') is None
+        assert t['B'] == []
+        with pytest.raises(ValueError):
+            t.reduce_all(prefix='B')
+        t.reduce_all(prefix='B', strict=False)
+        assert t.current_value('B').item() == 6.0 and t['B'] == []
+        t.next_epoch()
+        assert t['B'] == [torch.tensor(6.0)] and t['A'] == [None] and t.current_value('B') is None
+
+    def test_error_conventions(self):
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        with pytest.raises(ValueError):
+            t['nope']
+        with pytest.raises(ValueError):
+            t.track('nope', 1)
+        with pytest.raises(ValueError):
+            t.has_value('nope')
+        with pytest.raises(ValueError):
+            t.current_value('nope')
+        with pytest.raises(ValueError):
+            t.is_reduced_metric('nope')
+        t.register_metric('A', Reduction.SUM)
+        with pytest.raises(ValueError):
+            t.register_metric('A')
+        with pytest.raises(ValueError):
+            t.register_metric('B', dim=[0])
+        with pytest.raises(RuntimeError):  # mean of integers, as torch.mean would refuse
+            t.register_metric('C', Reduction.MEAN)
+            t.track('C', 3)
+
+    def test_int64_counters_and_dtypes(self):
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        t.register_metric('n', Reduction.SUM)
+        t.register_metric('m', Reduction.MAX)
+        t.register_metric('d', Reduction.MEAN)
+        for i in range(5):
+            t.track('n', 1)
+            t.track('m', torch.tensor(i, dtype=torch.int32))
+            t.track('d', torch.tensor(float(i), dtype=torch.float64))
+        t.next_epoch()
+        assert t['n'][0].dtype == torch.int64 and t['n'][0].item() == 5
+        assert t['m'][0].dtype == torch.int32 and t['m'][0].item() == 4
+        assert t['d'][0].dtype == torch.float64 and t['d'][0].item() == 2.0
+
+    def test_state_dict_roundtrip_mid_epoch(self):
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t1 = make_tracker()
+        t1.register_metric('A')
+        t1.register_metric('B', reduction=Reduction.MEAN, globally=False)
+        t1.track('A', 1)
+        t1.track('B', torch.randn(3, 2))
+        t1.next_epoch()
+        t1.track('A', 2)
+        x = torch.randn(3, 2)
+        t1.track('B', x)
+        state = t1.state_dict()
+        t2 = MetricTracker()
+        t2.bind(slab=OracleSlab())
+        t2.load_state_dict(state)
+        assert t2.epoch == t1.epoch and 'A' in t2 and 'B' in t2
+        assert t2['A'] == t1['A'] and t2['B'] == t1['B']
+        # the partially accumulated epoch continues identically on both
+        y = torch.randn(3, 2)
+        t1.track('B', y)
+        t2.track('B', y)
+        t1.next_epoch()
+        t2.next_epoch()
+        assert t1['B'][-1] == t2['B'][-1]
+        np.testing.assert_allclose(t1['B'][-1].item(), torch.stack([x, y]).mean().item(), rtol=1e-6)
+
+    def test_deferred_results_materialise_on_access(self):
+        from dmlcloud_b200.metrics import Reduction, _Deferred
+
+        t = make_tracker()
+        t.deferred = True
+        t.register_metric('x', Reduction.SUM)
+        t.track('x', 2.5)
+        t.next_epoch()
+        assert isinstance(t._histories['x'][0], _Deferred)  # nothing fetched yet
+        assert t['x'][0].item() == 2.5
+        assert isinstance(t._histories['x'][0], torch.Tensor)
+
+    def test_one_launch_per_reduce_all(self):
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        for i in range(50):
+            t.register_metric(f'm{i}', Reduction.MEAN)
+        for step in range(3):
+            for i in range(50):
+                t.track(f'm{i}', float(i + step))
+        t.next_epoch()
+        assert t._slab.launches == [('local', 50)]  # the reference would have issued 3 collectives per metric
+        assert t['m7'][0].item() == 8.0
+
+    def test_live_reduce_keeps_epoch_open(self):
+        from dmlcloud_b200.metrics import Reduction
+
+        t = make_tracker()
+        t.register_metric('loss', Reduction.MEAN)
+        t.track('loss', 1.0)
+        t.track('loss', 3.0)
+        live = t.reduce_live()
+        assert live['loss'].value().item() == 2.0
+        t.track('loss', 5.0)
+        t.next_epoch()
+        assert t['loss'][0].item() == 3.0
+
+    @pytest.mark.parametrize('world', [1])
+    def test_reference_session_fixture_w1(self, world):
+        from dmlcloud_b200.metrics import Reduction
+
+        gold = load_json(f'metrics_w{world}.json')
+        t = make_tracker()
+        replay_metric_script(t, gold['script'], 0, Reduction)
+        assert_histories_match(t.histories, t.epoch, gold['ranks'][0])
+
+
+# -------------------------------------------------------------------------------------------------------------- shards
+class TestShardingHost:
+    def test_reference_golden_lists(self):
+        from dmlcloud_b200.util.data import shard_indices
+
+        # reference test/test_data.py:24-54
+        out = shard_indices(10, 0, 2, shuffle=False, even_shards=False)
+        assert isinstance(out, list) and all(isinstance(i, int) for i in out)
+        assert shard_indices(10, 0, 2, even_shards=False) == [0, 2, 4, 6, 8]
+        assert shard_indices(10, 1, 3, even_shards=False) == [1, 4, 7]
+        assert shard_indices(11, 0, 2, even_shards=False) == [0, 2, 4, 6, 8, 10]
+        assert shard_indices(10, 2, 3, even_shards=True) == [2, 5, 8]
+        assert shard_indices(11, 0, 2, even_shards=True) == [0, 2, 4, 6, 8]
+        got = shard_indices(10, 0, 2, shuffle=True, even_shards=False, seed=0)
+        assert len(got) == 5 and len(set(got)) == 5 and got != sorted(got) and all(0 <= i <= 9 for i in got)
+
+    def test_matches_reference_fixture_and_c_oracle(self):
+        from dmlcloud_b200.util.data import ShardedSequenceDataset, shard_indices
+        from oracle import shard
+
+        gold = load_json('shard_indices.json')
+        for c in gold['cases']:
+            args = (c['n'], c['rank'], c['world'], c['shuffle'], c['even_shards'], c['seed'])
+            assert shard_indices(*args) == c['out'] == shard.shard_indices(*args)
+        for e in gold['epochs']:
+            ds = ShardedSequenceDataset(list(range(e['base'], e['base'] + e['len'])), shuffle=True, seed=e['seed'],
+                                        rank=e['rank'], world_size=e['world'])
+            ds.set_epoch(e['epoch'])
+            assert list(iter(ds)) == e['out']
+
+    def test_chunks_batches_interleave(self):
+        from dmlcloud_b200.util.data import BatchDataset, PrefetchDataset, chunk_and_shard_indices, interleave_batches
+
+        assert chunk_and_shard_indices(100, 10, 1, 3, chunk_overlap=2) == [(10, 22), (40, 52), (70, 82)]
+        assert chunk_and_shard_indices(95, 10, 0, 2, equal_chunks=False, even_shards=False)[-1] == (80, 90)
+        assert list(BatchDataset(list(range(7)), 3)) == [[0, 1, 2], [3, 4, 5], [6]]
+        assert len(BatchDataset(list(range(7)), 3, drop_remainder=True)) == 2
+        assert list(PrefetchDataset(list(range(20)), 4)) == list(range(20))
+        batches = [torch.arange(0, 8), torch.arange(8, 16), torch.arange(16, 24), torch.arange(24, 32)]
+        out = [t.clone() for t in interleave_batches(batches, num_batches=2)]
+        assert {t.item() for t in out[0]} == {0, 1, 2, 3, 8, 9, 10, 11}  # reference test/test_data.py:444-457
+        assert {t.item() for t in out[3]} == {20, 21, 22, 23, 28, 29, 30, 31}
+        assert [b.tolist() for b in interleave_batches(batches, 1)] == [b.tolist() for b in batches]
+
+
+# --------------------------------------------------------------------------------------------------- checkpoint / misc
+class TestCheckpointDir:
+    def test_layout_and_config(self, tmp_path, monkeypatch):
+        from dmlcloud_b200.checkpoint import CheckpointDir, find_slurm_checkpoint, generate_checkpoint_path, \
+            generate_id, sanitize_filename
+
+        assert sanitize_filename('a/b') == 'a_b'
+        assert '-' not in generate_id() and '_' not in generate_id()
+        p = generate_checkpoint_path(tmp_path, 'my/run')
+        assert p.parent == tmp_path and p.name.startswith('my_run-20')
+        d = CheckpointDir(p)
+        assert not d.exists and not d.is_valid
+        monkeypatch.setenv('SLURM_JOB_ID', '4242')
+        d.create()
+        assert d.is_valid and d.indicator_file.name == '.dmlcloud' and d.log_file.exists()
+        assert d.slurm_job_id == '4242' and find_slurm_checkpoint(tmp_path) == p
+        with pytest.raises(ValueError):
+            d.create()
+        d.save_config({'lr': 0.1, 'model': {'width': 16}})
+        assert d.load_config()['model']['width'] == 16
+        d.save_state({'x': torch.arange(3)}, 'latest')
+        assert d.has_state() and d.load_state()['x'].tolist() == [0, 1, 2]
+        with pytest.raises(ValueError):
+            CheckpointDir(tmp_path / 'missing').load_config()
+
+
+def _dummy_group():
+    from dmlcloud_b200.util.distributed import init_process_group_dummy
+
+    init_process_group_dummy(backend='gloo')
+
+
+class TestPipelineHost:
+    def test_dummy_group_and_helpers(self):
+        from dmlcloud_b200.util import distributed as D
+
+        _dummy_group()
+        try:
+            assert D.rank() == 0 and D.world_size() == 1 and D.local_rank() == 0 and D.is_root()
+            assert D.all_gather_object('x') == ['x'] and D.gather_object(3) == [3] and D.broadcast_object({'a': 1}) == {'a': 1}
+            with D.root_first():
+                pass
+            assert D.root_only(lambda: 5)() == 5
+        finally:
+            D.deinitialize_torch_distributed()
+        assert D.rank() is None
+
+    def test_pipeline_requires_cuda_and_pg(self):
+        from dmlcloud_b200 import Stage
+        from dmlcloud_b200.pipeline import TrainingPipeline
+
+        p = TrainingPipeline()
+        with pytest.raises(ValueError):
+            p.run()  # no stages
+        p.append_stage(Stage())
+        with pytest.raises(ValueError):
+            p.run()  # no process group
+        with pytest.raises(ValueError):
+            p.append_stage(object())
+        p.register_optimizer('o', object())
+        with pytest.raises(ValueError):
+            p.register_optimizer('o', object())
+        if not torch.cuda.is_available():
+            _dummy_group()
+            try:
+                with pytest.raises(RuntimeError, match='CUDA'):
+                    p.run()
+            finally:
+                from dmlcloud_b200.util.distributed import deinitialize_torch_distributed
+
+                deinitialize_torch_distributed()
+
+    def test_stage_loop_with_injected_engine(self, tmp_path, capsys):
+        """The TrainValStage step loop / epoch driver / checkpoint snapshots on CPU tensors, engine injected by the
+        test (device selection overridden; model not wrapped in DDP — the gradient path is GPU-only and tested there)."""
+        from dmlcloud_b200 import TrainValStage
+        from dmlcloud_b200.pipeline import TrainingPipeline
+
+        class CpuPipeline(TrainingPipeline):
+            def _select_device(self):
+                return torch.device('cpu')
+
+            def _bind_metric_path(self):
+                self.tracker.bind(slab=OracleSlab())
+
+        class S(TrainValStage):
+            def pre_stage(self):
+                torch.manual_seed(0)
+                self.model = torch.nn.Linear(10, 10)
+                self.pipeline.register_model('linear', self.model, use_ddp=False, save_interval=1)
+                self.pipeline.register_optimizer('sgd', torch.optim.SGD(self.model.parameters(), lr=1e-2))
+                data = [(torch.randn(4, 10), torch.randint(0, 10, (4,))) for _ in range(3)]
+                self.pipeline.register_dataset('train', data)
+                self.pipeline.register_dataset('val', data[:2])
+                self.loss = torch.nn.CrossEntropyLoss()
+
+            def step(self, batch):
+                x, y = batch
+                return self.loss(self.model(x), y)
+
+        _dummy_group()
+        try:
+            p = CpuPipeline(name='host')
+            p.enable_checkpointing(str(tmp_path))
+            with pytest.raises(ValueError):
+                p.enable_checkpointing(str(tmp_path))
+            stage = S()
+            p.append_stage(stage, max_epochs=2)
+            p.run()
+        finally:
+            from dmlcloud_b200.util.distributed import deinitialize_torch_distributed
+
+            deinitialize_torch_distributed()
+        t = p.tracker
+        assert t.epoch == 3 and stage.current_epoch == 3
+        assert [v.item() for v in t['misc/total_train_batches']] == [3, 3]
+        assert t['misc/total_train_batches'][0].dtype == torch.int64
+        assert [v.item() for v in t['misc/worker_val_batches']] == [2, 2]
+        assert t['misc/epoch'] == [1, 2] and len(t['train/loss']) == 2 and t['train/loss'][0].dtype == torch.float32
+        assert t['train/loss'][1] < t['train/loss'][0]
+        ck = p.checkpoint_dir
+        assert ck.is_valid and ck.has_state('latest') and ck.has_state('epoch_1') and ck.has_state('epoch_2')
+        state = ck.load_state('latest')
+        assert state['stage_epoch'] == 3 and state['tracker']['epoch'] == 3
+        assert '[Train] Loss' in (ck.log_file.read_text() + capsys.readouterr().out)
+
+
+# ------------------------------------------------------------------------------------------------------ W = 2 over gloo
+def _w2_metrics_worker(rank, world, initfile, outdir):
+    init_gloo(rank, world, initfile)
+    from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+    gold = load_json('metrics_w2.json')
+    t = MetricTracker()
+    t.bind(slab=OracleSlab())
+    replay_metric_script(t, gold['script'], rank, Reduction)
+    assert_histories_match(t.histories, t.epoch, gold['ranks'][rank])
+    exchanges = [k for k in t._slab.launches if k[0] == 'exchange']
+    n_reduce_calls = sum(1 for op in gold['script'] if op[0] in ('next_epoch', 'reduce_all'))
+    assert len(exchanges) <= n_reduce_calls  # at most one exchange per reduce_all / next_epoch, never one per metric
+
+    # split emptiness vote (reference metrics.py:124-128): only rank 0 tracks -> ValueError on every rank
+    t2 = MetricTracker()
+    t2.bind(slab=OracleSlab())
+    t2.register_metric('v', Reduction.MEAN)
+    t2.register_metric('local_only', Reduction.SUM, globally=False)
+    if rank == 0:
+        t2.track('v', 1.0)
+    t2.track('local_only', rank + 1)  # rank-local metrics may differ freely
+    try:
+        t2.next_epoch()
+        raised = False
+    except ValueError as e:
+        raised = 'Some workers tracked values' in str(e)
+    Path(outdir, f'ok{rank}').write_text(json.dumps({'raised': raised}))
+    import torch.distributed as dist
+
+    dist.destroy_process_group()
+
+
+def _w2_pipeline_worker(rank, world, initfile, outdir):
+    init_gloo(rank, world, initfile)
+    import torch.distributed as dist
+
+    from dmlcloud_b200 import TrainValStage
+    from dmlcloud_b200.pipeline import TrainingPipeline
+    from dmlcloud_b200.util import distributed as D
+    from dmlcloud_b200.util.data import ShardedSequenceDataset
+
+    class CpuPipeline(TrainingPipeline):
+        def _select_device(self):
+            return torch.device('cpu')
+
+        def _bind_metric_path(self):
+            self.tracker.bind(slab=OracleSlab())
+
+    class S(TrainValStage):
+        def pre_stage(self):
+            holder = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(()))])
+            self.pipeline.register_model('w', holder, use_ddp=False, verbose=False)
+            self.w = holder[0]
+            self.pipeline.register_optimizer('sgd', torch.optim.SGD([self.w], lr=0.1))
+            items = ShardedSequenceDataset(list(range(10)), shuffle=True, seed=5)  # rank/world from the group
+            self.pipeline.register_dataset('train', items)
+            self.pipeline.register_dataset('val', [0])
+
+        def pre_epoch(self):
+            self.pipeline.datasets['train'].set_epoch(self.current_epoch)
+            self.seen = []
+
+        def step(self, item):
+            self.seen.append(int(item))
+            self.track_reduce('item', float(item))
+            return (self.w - float(item)) ** 2
+
+        def post_epoch(self):
+            everyone = D.all_gather_object(self.seen[:5])
+            assert sorted(everyone[0] + everyone[1]) == list(range(10))  # the two shards partition the epoch
+
+    p = CpuPipeline(name='w2')
+    p.enable_checkpointing(outdir + '/ckpt')
+    assert len({str(x) for x in D.all_gather_object(str(p.checkpoint_dir))}) == 1  # rank 0's path was broadcast
+    s = S()
+    p.append_stage(s, max_epochs=2)
+    p.run()
+    t = p.tracker
+    assert [v.item() for v in t['misc/total_train_batches']] == [10, 10]
+    assert [v.item() for v in t['misc/worker_train_batches']] == [5, 5]
+    assert [round(v.item(), 5) for v in t['train/item']] == [4.5, 4.5]
+    if rank == 0:
+        assert p.checkpoint_dir.has_state('latest')
+    Path(outdir, f'done{rank}').write_text('ok')
+    dist.destroy_process_group()
+
+
+class TestWorldSize2:
+    def test_metric_session_and_vote_over_gloo(self):
+        out = spawn(_w2_metrics_worker, 2)
+        for r in range(2):
+            assert json.loads((out / f'ok{r}').read_text())['raised'] is True
+
+    def test_pipeline_stage_sharding_over_gloo(self):
+        out = spawn(_w2_pipeline_worker, 2)
+        assert (out / 'done0').exists() and (out / 'done1').exists()
