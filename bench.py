@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py — samples/sec of the MNIST-CNN data-parallel training step through dmlcloud_b200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 200 --warmup 20                       # native arm, one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                          # N ranks, one per GPU
+    python bench.py --impl reference --gpus N --steps K --warmup W         # the reference's CPU/gloo path (oracle port)
+
+A "step" = one pass of the hot path over one synthetic MNIST-shaped batch (32 samples per rank): zero_grad, forward
+(bf16 autocast), backward — DDP hands every gradient bucket to GradBucketSync.hook (libdmlb K1 -> exchange -> K2) —
+Adam, 5 tracked metrics folded into the device slab, and the cross-rank metric exchange (fused slab kernel) EVERY step.
+Everything goes through the public API: TrainingPipeline.run() -> TrainValStage.train_epoch().
+
+  value   inputs already resident in HBM (K distinct batches), device-timed with CUDA events, max over ranks
+  e2e     the same loop fed from pinned HOST memory: H2D copy of every batch and a D2H read of the step's reduced
+          metrics (the live exchange copies its result to pinned memory every step; the host reads it one step late)
+  roofline            libdmlb bucket kernel (dmlb_bucket_pack_f32_bf16) on a 1 GiB cold buffer, same C-ABI entry point
+  roofline_in_situ    the bucket launches inside the timed region (41 KB MNIST bucket: launch-latency bound)
+  cpu_baseline        oracle/ref_port.py — the reference's CPU path — on this box's host cores (rank 0, N=1 only)
+
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = 'samples/sec (box, device-timed) MNIST CNN'
+BATCH = 32
+SAMPLE_BYTES_IN = 1 * 28 * 28 * 4  # fp32 image
+LABEL_BYTES = 8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=30)
+    ap.add_argument('--impl', choices=['native', 'reference'], default='native')
+    ap.add_argument('--grad-wire', choices=['bf16', 'fp32'], default='bf16')
+    ap.add_argument('--grad-route', choices=['auto', 'peer', 'nccl'], default='auto')
+    ap.add_argument('--metric-route', choices=['auto', 'peer', 'collective'], default='auto')
+    ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=3000)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.path = Path(tempfile.mkdtemp(prefix='dmlb_clk_')) / 'clocks.csv'
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.gpu_index)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.path.read_text().splitlines():
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------------------------
+def native_arm(args):
+    import torch
+    import torch.distributed as dist
+    from torch import nn
+
+    from dmlcloud_b200 import TrainValStage, _native as N
+    from dmlcloud_b200.metrics import Reduction
+    from dmlcloud_b200.pipeline import TrainingPipeline
+    from dmlcloud_b200.util import distributed as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (native arm) needs CUDA: dmlcloud_b200 has no CPU fallback')
+    D.init_process_group_auto()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE is {world}: launch with torchrun --nproc-per-node {args.gpus}')
+    K, W = args.steps, max(3, args.warmup)
+    torch.backends.cudnn.benchmark = True
+
+    def gen_batches(seed, count, pinned):
+        g = torch.Generator().manual_seed(seed)
+        out = []
+        for _ in range(count):
+            x = torch.randn(BATCH, 1, 28, 28, generator=g)
+            y = torch.randint(0, 10, (BATCH,), generator=g)
+            out.append((x.pin_memory(), y.pin_memory()) if pinned else (x, y))
+        return out
+
+    class Phase:
+        def __init__(self, name, data, timed):
+            self.name, self.data, self.timed = name, data, timed
+            self.elapsed_ms = None
+            self.launches = 0
+            self.clocks = None
+
+    class BenchStage(TrainValStage):
+        def pre_stage(self):
+            dev = self.device
+            torch.manual_seed(0)
+            model = nn.Sequential(nn.Conv2d(1, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+                                  nn.Conv2d(16, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(),
+                                  nn.Linear(784, 10))  # reference examples/mnist.py:27-36
+            self.pipeline.register_model('cnn', model, verbose=False, grad_wire=args.grad_wire)
+            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3))
+            self.loss = nn.CrossEntropyLoss()
+            self.live_metrics_every = 1  # metrics cross ranks EVERY step (BASELINE configs 2/3)
+            self.tracker.deferred = True
+            host = gen_batches(100 + rank, W + K, pinned=True)
+            resident = [(x.to(dev), y.to(dev)) for x, y in host]
+            self.phases = [Phase('warmup', resident[:W], False), Phase('value', resident[W:], True),
+                           Phase('warmup_e2e', host[:W], False), Phase('e2e', host[W:], True)]
+            self.pipeline.datasets['train'] = []
+            self.pipeline.datasets['val'] = []
+            self.host_reads = 0
+            self.read_host = False
+
+        def step(self, batch):
+            x, y = batch
+            x = x.to(self.device, non_blocking=True)  # no-op for the resident phases
+            y = y.to(self.device, non_blocking=True)
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                out = self.pipeline.models['cnn'](x)
+            loss = self.loss(out.float(), y)
+            self.track_reduce('accuracy', (out.argmax(1) == y).float().mean())
+            if self.read_host and self.live_metrics:  # D2H read of the previous step's reduced metrics
+                self.last_loss = self.live_metrics['train/loss'].value()
+                self.host_reads += 1
+            return loss
+
+        def run_epoch(self):
+            phase = self.phases[self.current_epoch - 1]
+            self.pipeline.datasets['train'] = phase.data
+            self.read_host = phase.name == 'e2e'
+            sync = self.pipeline.grad_syncs['cnn']
+            sync.profile_events = phase.name == 'value'
+            if phase.timed:
+                sampler = ClockSampler(self.device.index)
+                dist.barrier()
+                torch.cuda.synchronize()
+                sampler.start()
+                n0 = N.launch_count()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                wall0 = time.perf_counter()
+                t0.record()
+            self.train_epoch()  # <- the public per-step loop (stage.py train_epoch), exactly len(phase.data) steps
+            if phase.timed:
+                t1.record()
+                torch.cuda.synchronize()
+                wall = (time.perf_counter() - wall0) * 1e3
+                dist.barrier()
+                phase.elapsed_ms = max(t0.elapsed_time(t1), 0.0)
+                phase.wall_ms = wall
+                phase.launches = N.launch_count() - n0
+                phase.clocks = sampler.stop()
+            sync.profile_events = False
+
+    pipeline = TrainingPipeline(name='bench')
+    pipeline.grad_route, pipeline.metric_route = args.grad_route, args.metric_route
+    stage = BenchStage()
+    pipeline.append_stage(stage, max_epochs=4)
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        pipeline.run()
+    dev = pipeline.device
+    value_phase, e2e_phase = stage.phases[1], stage.phases[3]
+
+    def max_over_ranks(ms):
+        box = [None] * world
+        dist.all_gather_object(box, ms)
+        return max(box)
+
+    value_ms = max_over_ranks(value_phase.elapsed_ms)
+    e2e_ms = max_over_ranks(max(e2e_phase.elapsed_ms, e2e_phase.wall_ms))  # host reads are part of e2e: wall >= device
+    samples = K * BATCH * world
+    sync = pipeline.grad_syncs['cnn']
+
+    # ---- in-situ bucket kernel timing (events recorded on the launching stream inside the value phase) ----
+    torch.cuda.synchronize()
+    durs = [a.elapsed_time(b) * 1e3 for a, b, _, _ in sync.event_log]  # us
+    n_elem = sync.event_log[0][2] if sync.event_log else 0
+    route = sync.event_log[0][3] if sync.event_log else None
+    per_elem = {('single', 'bf16'): 12, ('single', 'fp32'): 8, ('peer', 'bf16'): 12, ('peer', 'fp32'): 16,
+                ('nccl', 'bf16'): 12, ('nccl', 'fp32'): 8}.get((route, args.grad_wire), 12)
+    peaks = load_peaks()
+    in_situ = None
+    if durs:
+        mean_us = statistics.mean(durs)
+        achieved = n_elem * per_elem / (mean_us * 1e-6) / 1e9
+        in_situ = {'kernel': f'GradBucketSync[{route},{args.grad_wire}] bucket launches', 'elements': n_elem,
+                   'bound': 'hbm', 'achieved': round(achieved, 2), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                   'frac': round(achieved / peaks['hbm_gbs'], 5), 'mean_us': round(mean_us, 2),
+                   'algorithmic_bytes_per_launch': n_elem * per_elem, 'launches_timed': len(durs),
+                   'note': 'MNIST bucket = 10,330 fp32 (41 KB): launch-latency bound, not bandwidth bound'}
+
+    result = {
+        'metric': METRIC, 'value': round(samples / (value_ms * 1e-3), 1), 'unit': 'samples/s', 'n_gpus': world,
+        'steps': K, 'warmup': W, 'ms_per_step': round(value_ms / K, 4), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16' if args.grad_wire == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP, bf16 autocast, Adam, 32 samples/rank/step, '
+                               '5 metrics tracked + cross-rank metric exchange every step',
+                   'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'grad_wire': args.grad_wire,
+                   'grad_route': sorted(set(sync.last_routes.values())),
+                   'metric_route': 'peer' if pipeline.metric_comm is not None else ('single' if world == 1 else 'collective'),
+                   'l2': 'K distinct batches; the whole working set (<10 MB) is L2-resident by the nature of this '
+                         'workload; roofline microbench uses 1 GiB buffers (> 126 MB L2)'},
+        'clocks': value_phase.clocks,
+        'e2e': {'value': round(samples / (e2e_ms * 1e-3), 1), 'unit': 'samples/s',
+                'h2d_bytes_per_step': BATCH * (SAMPLE_BYTES_IN + LABEL_BYTES),
+                'd2h_bytes_per_step': 8 + 9 * pipeline.tracker._slab.capacity,
+                'ms_per_step': round(e2e_ms / K, 4), 'host_reads': stage.host_reads},
+        'gpu_launches': value_phase.launches,
+        'wall_ms_per_step': round(value_phase.wall_ms / K, 4),
+        'roofline_in_situ': in_situ,
+    }
+
+    if rank == 0 and not args.no_micro:
+        result.update(kernel_microbench(dev, peaks))
+    if not args.no_micro:
+        mr = metric_reduce_microbench(pipeline, dev, world, rank)
+        if rank == 0:
+            result['metric_reduce_us'] = mr
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result['cpu_baseline'] = cpu_baseline(args.cpu_steps)
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    for s in pipeline.grad_syncs.values():
+        s.close()
+    if pipeline.metric_comm is not None:
+        pipeline.metric_comm.close()
+    dist.destroy_process_group()
+
+
+def load_peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {'hbm_gbs': float(d['hbm_gbs']), 'source': 'MEASURED_PEAKS.json (of measured)'}
+    return {'hbm_gbs': 6650.0, 'source': 'B200_PROFILING.md fallback (of fallback)'}
+
+
+def kernel_microbench(dev, peaks):
+    """The bucket kernels through the C ABI on buffers far larger than L2 (1 GiB fp32 source), CUDA-event timed per launch
+    on the launching stream; plus the ResNet-18 bucket sizes with an L2 flush between launches."""
+    import torch
+
+    from dmlcloud_b200 import _native as N
+
+    lib = N.cuda_lib(dev.index)
+    n = 1 << 28  # 268,435,456 fp32 = 1 GiB
+    src = torch.empty(n, dtype=torch.float32, device=dev).normal_()
+    wire = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    st = N.stream_ptr()
+
+    def timed(fn, reps=10, warm=3, between=None):
+        for _ in range(warm):
+            fn()
+        out = []
+        for _ in range(reps):
+            if between:
+                between()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            out.append(a.elapsed_time(b) * 1e-3)
+        return out
+
+    def entry(name, bytes_per_elem, elems, secs, note=None):
+        mean = statistics.mean(secs)
+        ach = elems * bytes_per_elem / mean / 1e9
+        d = {'kernel': name, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+             'frac': round(ach / peaks['hbm_gbs'], 4), 'traffic': None, 'elements': elems,
+             'algorithmic_bytes_per_launch': elems * bytes_per_elem, 'mean_us': round(mean * 1e6, 2),
+             'best_us': round(min(secs) * 1e6, 2), 'peak_source': peaks['source']}
+        if note:
+            d['note'] = note
+        return d
+
+    pack = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
+    unpack = timed(lambda: N.check(lib.dmlb_bucket_unpack_bf16_f32(wire.data_ptr(), src.data_ptr(), n, 1.0, None, st)))
+    scale = timed(lambda: N.check(lib.dmlb_bucket_scale_f32(src.data_ptr(), n, 1.0, st)))
+    out = {
+        'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, n, pack,
+                          'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2)'),
+        'roofline_more': [entry('dmlb_bucket_unpack_bf16_f32 (K2)', 6, n, unpack),
+                          entry('dmlb_bucket_scale_f32 (K1, fp32 wire, in place)', 8, n, scale)],
+    }
+    # ResNet-18 DDP buckets, L2 flushed by a 512 MB write between launches
+    flush = torch.empty(128 << 20, dtype=torch.float32, device=dev)
+    buckets = []
+    for elems in (513_000, 7_213_056, 3_963_456, 11_689_512):
+        s = src[:elems]
+        w = wire[:elems]
+        secs = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(s.data_ptr(), w.data_ptr(), elems, 0.125, st)),
+                     reps=8, warm=2, between=lambda: flush.zero_())
+        buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, secs, 'L2 flushed before each launch'))
+    out['roofline_resnet18_buckets'] = buckets
+    del src, wire, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=200, warm=20):
+    """BASELINE config 5: 1024 scalar metrics; latency from "last value written" to "reduced slab + its D2H copy done",
+    CUDA events on the stream, every rank (max over ranks reported)."""
+    import torch
+    import torch.distributed as dist
+
+    from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+    ops = [Reduction.MEAN, Reduction.SUM, Reduction.MIN, Reduction.MAX]
+    t = MetricTracker()
+    t.bind(device=dev, comm=pipeline.metric_comm, group=None)
+    t.deferred = True
+    names = [f'm{i}' for i in range(n_metrics)]
+    for i, name in enumerate(names):
+        t.register_metric(name, ops[i % 4])
+    vals = torch.randn(n_metrics, generator=torch.Generator().manual_seed(rank)).tolist()
+    lat = []
+    for it in range(warm + iters):
+        for name, v in zip(names, vals):
+            t.track(name, v)  # python floats ride as kernel immediates (31 per fold launch)
+        t._slab.flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        a.record()
+        t.next_epoch()  # ONE fused finalise / exchange / combine launch + one D2H copy
+        b.record()
+        b.synchronize()
+        if it >= warm:
+            lat.append(a.elapsed_time(b) * 1e3)
+    t._materialize()
+    lat.sort()
+    mine = {'median': lat[len(lat) // 2], 'p99': lat[int(len(lat) * 0.99) - 1], 'min': lat[0]}
+    box = [None] * world
+    dist.all_gather_object(box, mine)
+    return {'n_metrics': n_metrics, 'world': world, 'iters': iters,
+            'median': round(max(b['median'] for b in box), 2), 'p99': round(max(b['p99'] for b in box), 2),
+            'min': round(max(b['min'] for b in box), 2), 'unit': 'us',
+            'what': 'CUDA-event time of MetricTracker.next_epoch(): fused reduce kernel + async D2H of the results'}
+
+
+def cpu_baseline(steps):
+    """The reference's CPU path (oracle/ref_port.py) on this box's host cores: bounded sample, W=1."""
+    from oracle import ref_port
+
+    cores = os.cpu_count() or 1
+    res = ref_port.run_baseline(world=1, steps=steps, warmup=50, total_threads=cores, per_step_reduce=True)
+    return {'value': round(res['samples_per_s'], 1), 'unit': 'samples/s', 'cores': res['cores'], 'kind': 'port',
+            'sample': f'{steps} training steps x 32 samples of the same MNIST-CNN workload (torch CPU, gloo W=1, '
+                      f'metrics reduced every step), {res["seconds"]:.1f} s',
+            'epoch_reduce_ms': round(res['epoch_reduce_ms'], 3)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle port: torch CPU + DDP/gloo + per-metric gloo
+    collectives) on this box's host cores, W = --gpus gloo ranks, all host threads.  Under torchrun only rank 0 works."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_PORT', 'MASTER_ADDR', 'LOCAL_WORLD_SIZE', 'GROUP_RANK'):
+        os.environ.pop(k, None)  # the baseline spawns its own gloo world over a file store
+    from oracle import ref_port
+
+    world = args.gpus
+    cores = os.cpu_count() or 1
+    res = ref_port.run_baseline(world=world, steps=args.steps, warmup=max(3, args.warmup), total_threads=cores,
+                                per_step_reduce=True)
+    value = round(res['samples_per_s'], 1)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': round(res['seconds'] / args.steps * 1e3, 4),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP over gloo on host cores, Adam, 32 samples/rank/'
+                               'step, metrics reduced across ranks every step (reference CPU path, oracle/ref_port.py)',
+                   'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'threads_per_rank': res['threads_per_rank']},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': res['cores'], 'kind': 'port',
+                         'sample': f'{args.steps} steps x {BATCH} samples x {world} ranks, {res["seconds"]:.2f} s'},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        reference_arm(a)
+    else:
+        native_arm(a)

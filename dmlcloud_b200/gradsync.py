@@ -137,6 +137,9 @@ class GradBucketSync:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device) if track_sumsq else None
         self.buckets_seen = 0
         self.last_routes = {}
+        # optional live timing of the bucket launches (bench.py): [(start_event, end_event, n_elements, route)]
+        self.profile_events = False
+        self.event_log = []
 
     # -- helpers -----------------------------------------------------------------------------------------------------
     def _stage_for(self, index, n):
@@ -162,6 +165,22 @@ class GradBucketSync:
 
     def reduce_bucket(self, buf, index=0):
         """Average the flat fp32 gradient bucket `buf` across ranks in place; returns a Future of `buf`."""
+        if not self.profile_events:
+            return self._reduce_bucket(buf, index)
+        # CUDA events on the stream the kernels are launched on (torch.cuda.Event only sees torch's current stream;
+        # the peer route runs on comm_stream, so the pair is recorded there)
+        peer = (self.world > 1 and self.comm is not None)
+        stream = self.comm_stream if peer else torch.cuda.current_stream(self.device)
+        if peer:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        fut = self._reduce_bucket(buf, index)
+        t1.record(stream)
+        self.event_log.append((t0, t1, buf.numel(), self.last_routes.get(index)))
+        return fut
+
+    def _reduce_bucket(self, buf, index=0):
         if buf.dtype != torch.float32 or not buf.is_contiguous():
             raise RuntimeError('GradBucketSync expects contiguous fp32 gradient buckets')
         lib = N.cuda_lib(self.device.index)  # runs on the autograd thread: per-thread device of libdmlb's runtime

@@ -861,13 +861,15 @@ class MetricTracker:
     def state_dict(self):
         return {
             'epoch': self.epoch,
-            'histories': dict(self.histories),
+            # per-metric lists are copied: the reference hands out its live lists (metrics.py:285), which lets a
+            # restored tracker and its source grow each other's histories
+            'histories': {name: list(history) for name, history in self.histories.items()},
             'reducers': {name: reducer.state_dict() for name, reducer in self.reducers.items()},
         }
 
     def load_state_dict(self, state):
         self.epoch = state['epoch']
-        self._histories = state['histories']
+        self._histories = {name: list(history) for name, history in state['histories'].items()}
         self.reducers = {}
         for name, reducer_state in state['reducers'].items():
             metric = SlabMetric(self, name)

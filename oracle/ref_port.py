@@ -1,0 +1,224 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  The timed CPU baseline ("port" of the reference's own CPU path).
+
+A torch-CPU / gloo restatement of what the reference executes per training step and per epoch on its own CPU path
+(/root/reference does not exist on the GPU box, and a Python reference cannot be compiled into oracle/_ref):
+
+  stage.py:290-318   TrainValStage.train_epoch   zero_grad -> step -> loss.backward() [DDP over gloo] -> optimizer.step
+                                                 -> 4x track_reduce
+  metrics.py:66-73   MetricReducer.append        torch.as_tensor(v).detach().cpu(); list append
+  metrics.py:107-141 reduce_locally / reduce_globally   stack + mean/sum/amin/amax; all_gather_object vote; all_reduce
+  metrics.py:249-280 MetricTracker.reduce_all / next_epoch   one pass over all metrics, 3 gloo collectives per metric
+  pipeline.py:70-75  register_model              DistributedDataParallel(model, broadcast_buffers=False)
+
+Used by bench.py only: `cpu_baseline` (N=1, rank 0, bounded sample) and `--impl reference` (W gloo ranks on the host
+cores).  It is the thing being TIMED there as the baseline — never the product, never a fallback.
+Checked against the unmodified reference in the build container by tests/test_oracle_pins.py::TestRefPort (same seeds ->
+same tracker histories as tests/golden/train_w*.json).
+"""
+import os
+import time
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+MEAN, SUM, MIN, MAX = 'MEAN', 'SUM', 'MIN', 'MAX'
+_TORCH_OP = {SUM: dist.ReduceOp.SUM, MIN: dist.ReduceOp.MIN, MAX: dist.ReduceOp.MAX}
+
+
+def _local_reduce(t, reduction, dim):
+    """metrics.py:24-41"""
+    dims = list(range(t.dim())) if dim is None else dim
+    return {MEAN: t.mean, SUM: t.sum, MIN: t.amin, MAX: t.amax}[reduction](dims)
+
+
+class RefReducer:
+    """metrics.py:44-155 (the parts the training loop exercises)."""
+
+    def __init__(self, reduction=MEAN, dim=None, globally=True):
+        self.values, self.reduction, self.globally = [], reduction, globally
+        self.dim = [dim] if isinstance(dim, int) else (list(dim) if dim is not None else None)
+
+    def append(self, value):
+        self.values.append(torch.as_tensor(value).detach().cpu())
+
+    def reduce_locally(self):
+        if not self.values:
+            return None
+        dim = None if self.dim is None else [0] + [d + 1 for d in self.dim]
+        return _local_reduce(torch.stack(self.values), self.reduction, dim)
+
+    def reduce_globally(self, group=None):
+        if self.globally:
+            votes = [None] * dist.get_world_size(group)
+            dist.all_gather_object(votes, len(self.values) == 0, group=group)
+            if any(votes):
+                if len(votes) > 1 and not all(votes):
+                    raise ValueError('Some workers tracked values this epoch and some did not. This is likely a bug.')
+                return None
+        elif not self.values:
+            return None
+        t = self.reduce_locally()
+        if self.globally:
+            if self.reduction == MEAN:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                t /= dist.get_world_size(group)
+            else:
+                dist.all_reduce(t, op=_TORCH_OP[self.reduction], group=group)
+        return t
+
+
+class RefTracker:
+    """metrics.py:158-306 (register / track / reduce_all / next_epoch)."""
+
+    def __init__(self):
+        self.histories, self.reducers, self.epoch = {}, {}, 1
+
+    def has_value(self, name):
+        return len(self.histories[name]) >= self.epoch
+
+    def track_reduce(self, name, value, reduction=MEAN, dim=None, globally=True):
+        """pipeline.py:166-178 + metrics.py:232-247"""
+        if name not in self.histories:
+            self.histories[name] = [None] * (self.epoch - 1)
+            self.reducers[name] = RefReducer(reduction, dim, globally)
+        if isinstance(value, torch.Tensor):
+            value = value.detach().to('cpu', non_blocking=True)
+        if self.has_value(name):
+            raise ValueError(f'History for {name} already has a value for epoch {self.epoch}')
+        self.reducers[name].append(value)
+
+    def track(self, name, value):
+        if name not in self.histories:
+            self.histories[name] = [None] * (self.epoch - 1)
+        if self.has_value(name):
+            raise ValueError(f'History for {name} already has a value for epoch {self.epoch}')
+        self.histories[name].append(value)
+
+    def next_epoch(self):
+        for name, history in self.histories.items():
+            if self.has_value(name):
+                continue
+            reducer = self.reducers.get(name)
+            if reducer is None:
+                history.append(None)
+            else:
+                history.append(reducer.reduce_globally())
+                reducer.values.clear()
+        self.epoch += 1
+
+
+def mnist_cnn():
+    """examples/mnist.py:27-36 (10,330 parameters)."""
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Conv2d(1, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+                         nn.Conv2d(16, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(), nn.Linear(784, 10))
+
+
+def synthetic_batches(seed, steps, batch=32):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(batch, 1, 28, 28, generator=g), torch.randint(0, 10, (batch,), generator=g))
+            for _ in range(steps)]
+
+
+class RefRun:
+    """One rank of the reference's MNIST-CNN TrainValStage run on CPU tensors (DDP over gloo when world > 1)."""
+
+    def __init__(self, use_ddp=True):
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.tracker = RefTracker()
+        model = mnist_cnn()
+        self.raw_model = model
+        self.model = nn.parallel.DistributedDataParallel(model, broadcast_buffers=False) if use_ddp else model
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)
+        self.loss = nn.CrossEntropyLoss()
+        self.current_epoch = 1
+
+    def step(self, batch, prefix):
+        img, target = batch
+        output = self.model(img)
+        loss = self.loss(output, target)
+        self.tracker.track_reduce(f'{prefix}/accuracy', (output.argmax(1) == target).float().mean())  # mnist.py:50
+        return loss
+
+    def train_epoch(self, batches):
+        """stage.py:290-318"""
+        for batch in batches:
+            t0 = time.perf_counter_ns()
+            self.optimizer.zero_grad()
+            loss = self.step(batch, 'train')
+            loss.backward()
+            self.optimizer.step()
+            t1 = time.perf_counter_ns()
+            self.tracker.track_reduce('train/loss', loss)
+            self.tracker.track_reduce('misc/total_train_batches', torch.tensor(1), reduction=SUM)
+            self.tracker.track_reduce('misc/worker_train_batches', torch.tensor(1), reduction=SUM, globally=False)
+            self.tracker.track_reduce('misc/step_time_ms', torch.tensor(t1 - t0) / 1e6)
+
+    @torch.no_grad()
+    def val_epoch(self, batches):
+        """stage.py:320-335"""
+        for batch in batches:
+            loss = self.step(batch, 'val')
+            self.tracker.track_reduce('val/loss', loss)
+            self.tracker.track_reduce('misc/total_val_batches', torch.tensor(1), reduction=SUM)
+            self.tracker.track_reduce('misc/worker_val_batches', torch.tensor(1), reduction=SUM, globally=False)
+
+    def end_epoch(self, seconds=0.0):
+        """stage.py:172-185"""
+        self.tracker.track('misc/epoch', self.current_epoch)
+        self.tracker.track('misc/epoch_time', seconds)
+        self.tracker.next_epoch()
+        self.current_epoch += 1
+
+
+def timed_worker(rank, world, initfile, steps, warmup, threads, out_path, per_step_reduce):
+    """One gloo rank of the baseline: `warmup` untimed steps, then `steps` timed steps; rank 0 writes the result."""
+    import json
+
+    torch.set_num_threads(max(1, threads))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('gloo', init_method=f'file://{initfile}', rank=rank, world_size=world)
+    run = RefRun(use_ddp=True)
+    data = synthetic_batches(100 + rank, warmup + steps)
+    run.train_epoch(data[:warmup])
+    run.end_epoch()
+    dist.barrier()
+    t0 = time.perf_counter()
+    if per_step_reduce:  # the stricter operating point: metrics cross ranks every step
+        for b in data[warmup:]:
+            run.train_epoch([b])
+            run.end_epoch()
+    else:
+        run.train_epoch(data[warmup:])
+    dist.barrier()
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    run.end_epoch()
+    reduce_s = time.perf_counter() - t1
+    if rank == 0:
+        with open(out_path, 'w') as f:
+            json.dump({'seconds': dt, 'steps': steps, 'world': world, 'threads_per_rank': threads,
+                       'samples_per_s': steps * 32 * world / dt, 'epoch_reduce_ms': reduce_s * 1e3,
+                       'n_metrics': len(run.tracker.histories)}, f)
+    dist.destroy_process_group()
+
+
+def run_baseline(world, steps, warmup, total_threads=None, per_step_reduce=False):
+    """Launch `world` gloo ranks on this host's cores and return rank 0's timing dict."""
+    import json
+    import tempfile
+
+    import torch.multiprocessing as mp
+
+    cores = total_threads or os.cpu_count() or 1
+    threads = max(1, cores // world)
+    tmp = tempfile.mkdtemp(prefix='dmlb_ref_')
+    out = os.path.join(tmp, 'result.json')
+    mp.spawn(timed_worker, args=(world, os.path.join(tmp, 'init'), steps, warmup, threads, out, per_step_reduce),
+             nprocs=world, join=True)
+    with open(out) as f:
+        res = json.load(f)
+    res['cores'] = threads * world
+    return res

@@ -1,0 +1,189 @@
+"""GPU parity of the gradient-bucket path: GradBucketSync (DDP comm hook) + the fused peer all-reduce kernel.
+
+Inputs and expected outputs come from the unmodified reference running DDP over gloo (tests/golden/grads_*.npz: every
+rank's local gradients and the gradients DDP left in .grad), plus the numpy oracle for bit-exactness of the rank-ordered
+sums.  W>1 runs as W processes sharing cuda:0 — the peer arenas are mapped through CUDA IPC exactly as across NVLink.
+Tolerances are SURVEY §8d's: fp32 wire 1e-6*max|g|, bf16 wire 1e-2*max|g|; bit-exact against the oracle.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz
+from helpers import init_gloo, spawn
+from oracle import grad_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def torch_distributed():
+    from dmlcloud_b200.util.distributed import deinitialize_torch_distributed, init_process_group_dummy
+
+    init_process_group_dummy()
+    yield
+    deinitialize_torch_distributed()
+
+
+class TestSingleRank:
+    def test_hook_w1_fp32_is_identity_and_bf16_rounds(self, torch_distributed):
+        from dmlcloud_b200.gradsync import GradBucketSync
+
+        z = load_npz('grads_linear64_w1.npz')
+        g = z['local'][0, 0]
+        for wire, want in (('fp32', g), ('bf16', grad_oracle.round_bf16(g))):
+            sync = GradBucketSync('cuda:0', wire=wire, track_sumsq=True)
+            buf = torch.from_numpy(g.copy()).cuda()
+            out = sync.reduce_bucket(buf, 0).wait()
+            got = (out[0] if isinstance(out, (list, tuple)) else out).cpu().numpy()
+            assert (got == want).all()
+            np.testing.assert_allclose(sync.sumsq.item(), np.sum(want.astype(np.float64) ** 2), rtol=1e-12)
+            assert sync.last_routes[0] == 'single'
+
+    @pytest.mark.parametrize('wire', ['fp32', 'bf16'])
+    def test_ddp_with_hook_matches_plain_autograd(self, torch_distributed, wire):
+        """DistributedDataParallel + GradBucketSync.hook at W=1 == local gradients (fp32) / their bf16 rounding."""
+        import copy
+
+        from torch.nn.parallel import DistributedDataParallel
+
+        from dmlcloud_b200.gradsync import GradBucketSync
+
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Conv2d(1, 16, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool2d(2),
+                                    torch.nn.Flatten(), torch.nn.Linear(16 * 14 * 14, 10)).cuda()
+        shadow = copy.deepcopy(model)
+        ddp = DistributedDataParallel(model, broadcast_buffers=False, device_ids=[torch.device('cuda', 0)])
+        sync = GradBucketSync('cuda:0', wire=wire)
+        seen = []
+
+        def checking_hook(state, bucket):
+            before = bucket.buffer().clone()  # what DDP hands over: the raw local gradients of this bucket
+            fut = sync.hook(state, bucket)
+
+            def verify(f):
+                out = f.value()
+                out = out[0] if isinstance(out, (list, tuple)) else out
+                want = before if wire == 'fp32' else before.to(torch.bfloat16).float()
+                seen.append(bool(torch.equal(out, want)))  # W=1: identity (fp32) / one bf16 rounding — every bit
+                return out
+
+            return fut.then(verify)
+
+        ddp.register_comm_hook(sync, checking_hook)
+        x = torch.randn(8, 1, 28, 28, device='cuda')
+        y = torch.randint(0, 10, (8,), device='cuda')
+        for _ in range(3):  # DDP rebuilds its buckets after the first iteration: the hook must not cache layouts
+            for m in (ddp, shadow):
+                m.zero_grad()
+                torch.nn.functional.cross_entropy(m(x), y).backward()
+            # against an independent backward pass only to cuDNN's run-to-run reproducibility (atomics in wgrad)
+            for p, q in zip(model.parameters(), shadow.parameters()):
+                tol = 1e-5 if wire == 'fp32' else 1e-2
+                assert (p.grad - q.grad).abs().max() <= tol * q.grad.abs().max()
+        assert seen and all(seen)
+        assert sync.buckets_seen >= 3
+
+
+def _allreduce_worker(rank, world, initfile, outdir, cases):
+    init_gloo(rank, world, initfile)
+    import torch.distributed as dist
+
+    from dmlcloud_b200 import _native as N
+    from dmlcloud_b200.gradsync import WIRES, GradBucketSync
+
+    torch.cuda.set_device(0)
+    results = {}
+    syncs = {w: GradBucketSync('cuda:0', wire=w, route='peer', max_message_bytes=8 << 20, track_sumsq=True)
+             for w in ('fp32', 'bf16')}
+    lib = N.cuda_lib(0)
+    for name, wire, algo, source in cases:
+        if source.startswith('golden:'):
+            z = np.load(Path(__file__).parent / 'golden' / source[7:])
+            locals_ = z['local']  # [S, W, N]
+            reduced = z['reduced']
+        else:  # synthetic: n elements, deterministic per rank
+            n = int(source)
+            locals_ = np.stack([np.stack([np.random.RandomState(1000 * s + r).randn(n).astype(np.float32) * 3
+                                          for r in range(world)]) for s in range(2)])
+            reduced = None
+        sync = syncs[wire]
+        for s in range(locals_.shape[0]):
+            buf = torch.from_numpy(locals_[s, rank].copy()).cuda()
+            sync.zero_sumsq()
+            if algo == 0:
+                fut = sync.reduce_bucket(buf, 0)
+                fut.wait()
+            else:  # force one-shot (1) / two-shot (2) regardless of size
+                N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), buf.numel(), WIRES[wire], 1.0 / world,
+                                                sync.sumsq.data_ptr(), algo, N.stream_ptr()), 'allreduce')
+            torch.cuda.synchronize()
+            got = buf.cpu().numpy()
+            twoshot = algo == 2 or (algo == 0 and world > 2 and buf.numel() * (2 if wire == 'bf16' else 4) > 512 * 1024)
+            want = grad_oracle.allreduce_f32(locals_[s]) if wire == 'fp32' else \
+                grad_oracle.allreduce_bf16(locals_[s], round_result=twoshot)
+            key = f'{name}/{s}'
+            results[key] = {
+                'bit_exact_vs_oracle': bool((got == want).all()),
+                'max_abs_vs_oracle': float(np.abs(got - want).max()),
+                'sumsq_rel': float(abs(sync.sumsq.item() - np.sum(got.astype(np.float64) ** 2)) /
+                                   max(np.sum(got.astype(np.float64) ** 2), 1e-300)),
+            }
+            if reduced is not None:
+                scale = float(np.abs(reduced[s]).max())
+                results[key]['rel_vs_reference'] = float(np.abs(got - reduced[s]).max() / scale)
+            np.save(Path(outdir, f'{name.replace("/", "_")}_{s}_r{rank}.npy'), got)
+    Path(outdir, f'res{rank}.json').write_text(json.dumps(results))
+    dist.barrier()
+    for sync in syncs.values():
+        sync.close()
+    dist.destroy_process_group()
+
+
+def _check(world, cases, tol):
+    out = spawn(_allreduce_worker, world, cases, timeout=900)
+    res = [json.loads((out / f'res{r}.json').read_text()) for r in range(world)]
+    for key in res[0]:
+        name = key.split('/')[0]
+        for r in range(world):
+            e = res[r][key]
+            assert e['bit_exact_vs_oracle'], (key, r, e)  # rank-ordered fp32 sum == oracle, every bit
+            assert e['sumsq_rel'] < 1e-12, (key, e)
+            if 'rel_vs_reference' in e:
+                assert e['rel_vs_reference'] <= tol[name.split(':')[0]], (key, e)
+        # every rank ends with bit-identical gradients (replicas must not drift)
+        s = key.split('/')[1]
+        ref = np.load(out / f'{name.replace("/", "_")}_{s}_r0.npy')
+        for r in range(1, world):
+            assert (np.load(out / f'{name.replace("/", "_")}_{s}_r{r}.npy') == ref).all(), key
+
+
+TOL = {'fp32': 1e-6, 'bf16': 1e-2}
+
+
+@pytest.mark.parametrize('world', [2, 3, 4, 8])
+def test_fused_allreduce_vs_reference_ddp_linear64(world):
+    f = f'golden:grads_linear64_w{world}.npz'
+    _check(world, [('fp32:gold', 'fp32', 0, f), ('bf16:gold', 'bf16', 0, f)], TOL)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_fused_allreduce_vs_reference_ddp_mnist_cnn(world):
+    f = f'golden:grads_mnist_cnn_w{world}.npz'
+    _check(world, [('fp32:gold', 'fp32', 0, f), ('bf16:gold', 'bf16', 0, f),
+                   ('fp32:two', 'fp32', 2, f), ('bf16:two', 'bf16', 2, f)], TOL)
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_fused_allreduce_sizes_and_algorithms(world):
+    """Ragged sizes, both algorithms forced, a ResNet-18-bucket-sized message through the two-shot path."""
+    cases = []
+    for n in (1, 7, 9, 4097, 513000):
+        for wire in ('fp32', 'bf16'):
+            for algo in (1, 2):
+                cases.append((f'{wire}:n{n}a{algo}', wire, algo, str(n)))
+    cases.append(('bf16:big', 'bf16', 0, str(3_963_456)))  # ResNet-18 bucket 3 (15.1 MiB fp32)
+    _check(world, cases, TOL)

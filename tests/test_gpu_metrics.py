@@ -1,0 +1,284 @@
+"""GPU parity of the metric path (libdmlb K3/K4 behind dmlcloud_b200.metrics) against the reference's own unit vectors
+(reference test/test_metrics.py), the golden sessions produced by the unmodified reference (tests/golden/metrics_w*.json)
+and the numpy slab oracle (oracle/slab_oracle.py)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_json
+from helpers import assert_histories_match, init_gloo, replay_metric_script, spawn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def torch_distributed():
+    from dmlcloud_b200.util.distributed import deinitialize_torch_distributed, init_process_group_dummy
+
+    init_process_group_dummy()
+    yield
+    deinitialize_torch_distributed()
+
+
+def cuda(x, dtype=torch.float):
+    return torch.tensor(x, dtype=dtype, device='cuda')
+
+
+class TestMetricReducerOnGpu:
+    """reference test/test_metrics.py:8-89, values on the GPU"""
+
+    def _filled(self, globally):
+        from dmlcloud_b200.metrics import MetricReducer, Reduction
+
+        r = MetricReducer(reduction=Reduction.MIN, globally=globally)
+        r.append(cuda([1, 2, 3]))
+        r.append(cuda([-1, -2, -3]))
+        r.append(cuda([1, 7, 10]))
+        return r
+
+    def _check_all(self, r):
+        from dmlcloud_b200.metrics import Reduction
+
+        for red, want in ((Reduction.MIN, -3), (Reduction.MAX, 10), (Reduction.SUM, 18), (Reduction.MEAN, 2)):
+            r.reduction = red
+            assert r.reduce_locally().item() == want
+            assert r.reduce_globally().item() == want
+
+    def test_local_reduction(self):
+        self._check_all(self._filled(False))
+
+    def test_global_reduction(self, torch_distributed):
+        self._check_all(self._filled(True))
+
+    def test_partial_reduction(self):
+        from dmlcloud_b200.metrics import MetricReducer, Reduction
+
+        t = cuda([[[1, 2, 3], [4, 5, 6]], [[1, 2, 3], [4, 5, 6]]])
+        r = MetricReducer(reduction=Reduction.MIN, globally=False, dim=[1, 2])
+        r.append(t)
+        out = r.reduce_locally()
+        assert out.shape == (2,) and out.tolist() == [1, 1]
+        r = MetricReducer(reduction=Reduction.SUM, globally=False, dim=2)
+        r.append(t)
+        out = r.reduce_locally()
+        assert out.shape == (2, 2) and out.tolist() == [[6, 15], [6, 15]]
+        r = MetricReducer(reduction=Reduction.MAX, globally=False, dim=[0])  # leading dim: needs the permute path
+        r.append(t)
+        r.append(t * 2)
+        assert r.reduce_locally().tolist() == [[2, 4, 6], [8, 10, 12]]
+
+    def test_serialization_and_empty(self, torch_distributed):
+        from dmlcloud_b200.metrics import MetricReducer, Reduction
+
+        r = MetricReducer(reduction=Reduction.MIN, dim=(1, 2, 3))
+        r.append(torch.tensor([1, 2, 3]))
+        r2 = MetricReducer()
+        r2.load_state_dict(r.state_dict())
+        assert r2.reduction == Reduction.MIN and r2.dim == [1, 2, 3] and r2.values == r.values
+        e = MetricReducer(reduction=Reduction.MIN, globally=True)
+        assert e.reduce_locally() is None and e.reduce_globally() is None
+
+    def test_reduce_tensor(self):
+        from dmlcloud_b200.metrics import Reduction, reduce_tensor
+
+        x = torch.randn(4, 33, 5, device='cuda')
+        torch.testing.assert_close(reduce_tensor(x, Reduction.MEAN), x.mean(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(reduce_tensor(x, Reduction.SUM, dim=[1]), x.sum(1), rtol=1e-5, atol=1e-5)
+        assert torch.equal(reduce_tensor(x, Reduction.MIN, dim=[0, 2]), x.amin((0, 2)))
+        assert torch.equal(reduce_tensor(x, Reduction.MAX, dim=2), x.amax(2))
+        i = torch.randint(-100, 100, (7, 9), device='cuda')
+        assert torch.equal(reduce_tensor(i, Reduction.SUM), i.sum()) and reduce_tensor(i, Reduction.SUM).dtype == torch.int64
+        assert torch.equal(reduce_tensor(i, Reduction.MIN, dim=[1]), i.amin(1))
+        with pytest.raises(ValueError):
+            reduce_tensor([1, 2], Reduction.SUM)
+        with pytest.raises(RuntimeError):
+            reduce_tensor(i, Reduction.MEAN)
+        nan = cuda([1.0, float('nan'), 3.0])
+        assert torch.isnan(reduce_tensor(nan, Reduction.MIN)) and torch.isnan(reduce_tensor(nan, Reduction.MAX))
+
+
+class TestMetricTrackerOnGpu:
+    """reference test/test_metrics.py:91-204 + golden sessions"""
+
+    def test_track_epochs_strict_prefix(self):
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t = MetricTracker()
+        t.register_metric('A')
+        t.track('A', 1)
+        with pytest.raises(ValueError):
+            t.track('A', 42)
+        t.next_epoch()
+        t.track('A', 42)
+        t.register_metric('B', reduction=Reduction.MEAN, globally=False)
+        for v in (2.0, 4.0, 1.0, 1.0):
+            t.track('B', v)
+        t.next_epoch()
+        assert t['A'] == [1, 42] and t['B'] == [None, torch.tensor(2.0)]
+
+        t = MetricTracker()
+        t.register_metric('A')
+        t.register_metric('B', reduction=Reduction.SUM, globally=False)
+        for v in (1.0, 2.0, 3.0):
+            t.track('B', cuda(v))
+        t.reduce_all(prefix='B')
+        assert t.has_value('B') and not t.has_value('A') and t.current_value('B').item() == 6.0
+        assert not t.current_value('B').is_cuda  # histories hold CPU tensors like the reference's
+        with pytest.raises(ValueError):
+            t.reduce_all(prefix='B')
+        t.reduce_all(prefix='B', strict=False)
+        t.next_epoch()
+        assert t['B'] == [torch.tensor(6.0)] and t['A'] == [None]
+
+    def test_state_dict_roundtrip(self):
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t1 = MetricTracker()
+        t1.register_metric('A')
+        t1.register_metric('B', reduction=Reduction.MEAN, globally=False)
+        t1.track('A', 1)
+        t1.track('B', torch.randn(3, 2, device='cuda'))
+        t1.next_epoch()
+        t1.track('A', 2)
+        x = torch.randn(3, 2, device='cuda')
+        t1.track('B', x)
+        t2 = MetricTracker()
+        t2.load_state_dict(t1.state_dict())
+        assert t2.epoch == t1.epoch and t2['A'] == t1['A'] and t2['B'] == t1['B']
+        y = torch.randn(3, 2, device='cuda')
+        for t in (t1, t2):
+            t.track('B', y)
+            t.next_epoch()
+        assert torch.equal(t1['B'][-1], t2['B'][-1])
+        torch.testing.assert_close(t1['B'][-1], torch.stack([x, y]).mean().cpu(), rtol=1e-6, atol=1e-7)
+
+    def test_no_host_sync_while_tracking(self):
+        """The per-step path must not synchronise: track() while a long kernel is still running on the stream."""
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t = MetricTracker()
+        t.deferred = True
+        t.register_metric('x', Reduction.MEAN)
+        t.track('x', cuda(0.0))  # allocate cells etc. outside the measured region
+        torch.cuda.synchronize()
+        big = torch.randn(8192, 8192, device='cuda')
+        done = torch.cuda.Event()
+        for _ in range(20):
+            big = big @ big * 1e-4
+        for i in range(50):
+            t.track('x', big[0, 0])
+            t.track('x', float(i))
+        t.reduce_live()
+        t.next_epoch()
+        done.record()
+        assert not done.query(), 'tracking / reducing blocked on the GPU: the step loop would stall'
+        torch.cuda.synchronize()
+        assert t['x'][0] is not None
+
+    def test_session_fixture_w1_and_slab_oracle_bit_exact(self):
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+        from oracle.slab_oracle import OracleSlab
+
+        gold = load_json('metrics_w1.json')
+        dev = MetricTracker()
+        replay_metric_script(dev, gold['script'], 0, Reduction, device='cuda')
+        assert_histories_match(dev.histories, dev.epoch, gold['ranks'][0])  # vs the unmodified reference
+        ora = MetricTracker()
+        ora.bind(slab=OracleSlab())
+        replay_metric_script(ora, gold['script'], 0, Reduction)
+        assert_histories_match(dev.histories, dev.epoch,  # vs the numpy restatement of the slab: every bit
+                               {'epoch': ora.epoch, 'histories': {k: [_enc(v) for v in h] for k, h in ora.histories.items()}},
+                               exact_float=True)
+
+    def test_1024_metrics_one_launch(self):
+        from dmlcloud_b200 import _native as N
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t = MetricTracker()
+        ops = [Reduction.MEAN, Reduction.SUM, Reduction.MIN, Reduction.MAX]
+        vals = torch.randn(3, 1024, device='cuda')
+        for i in range(1024):
+            t.register_metric(f'm{i}', ops[i % 4])
+        for s in range(3):
+            for i in range(1024):
+                t.track(f'm{i}', vals[s, i])
+        before = N.launch_count()
+        t.next_epoch()
+        assert N.launch_count() - before == 1  # reference: 3 collectives per metric (metrics.py:121-141)
+        v = vals.cpu()
+        for i in (0, 1, 2, 3, 513, 1023):
+            want = [v[:, i].mean(), v[:, i].sum(), v[:, i].min(), v[:, i].max()][i % 4]
+            torch.testing.assert_close(t[f'm{i}'][0], want, rtol=1e-5, atol=1e-6)
+
+
+def _enc(v):
+    if v is None:
+        return None
+    if isinstance(v, torch.Tensor):
+        return {'dtype': str(v.dtype).replace('torch.', ''), 'shape': list(v.shape), 'data': v.flatten().tolist()}
+    return {'py': v}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# W > 1 on ONE GPU: ranks are separate processes sharing cuda:0; the exchange runs over CUDA-IPC mapped peer memory,
+# i.e. the same kernel and protocol as over NVLink (NCCL cannot put two ranks on one device, the peer path can).
+# ----------------------------------------------------------------------------------------------------------------------
+def _metrics_peer_worker(rank, world, initfile, outdir, route):
+    init_gloo(rank, world, initfile)
+    import torch.distributed as dist
+
+    from dmlcloud_b200.gradsync import PeerComm
+    from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    comm = PeerComm(dev, None, max_message_bytes=1 << 20) if route == 'peer' else None
+    gold = load_json(f'metrics_w{world}.json')
+    t = MetricTracker()
+    t.bind(device=dev, comm=comm, group=None)
+    replay_metric_script(t, gold['script'], rank, Reduction, device=dev)
+    assert_histories_match(t.histories, t.epoch, gold['ranks'][rank])
+
+    # split vote: only rank 0 tracks -> every rank raises the reference's ValueError (metrics.py:127-128)
+    t2 = MetricTracker()
+    t2.bind(device=dev, comm=comm, group=None)
+    t2.register_metric('v', Reduction.MEAN)
+    t2.register_metric('mine', Reduction.SUM, globally=False)
+    t2.track('mine', rank + 1)
+    if rank == 0:
+        t2.track('v', 1.0)
+    try:
+        t2.next_epoch()
+        raised = False
+    except ValueError as e:
+        raised = 'Some workers tracked values' in str(e)
+    # and a count-lane vote: cells exist everywhere, but rank 1 tracked nothing this epoch
+    t3 = MetricTracker()
+    t3.bind(device=dev, comm=comm, group=None)
+    t3.register_metric('v', Reduction.MEAN)
+    t3.track('v', float(rank))
+    t3.next_epoch()
+    assert t3['v'][0].item() == sum(range(world)) / world
+    if rank != 1:
+        t3.track('v', 1.0)
+    try:
+        t3.next_epoch()
+        raised3 = False
+    except ValueError:
+        raised3 = True
+    Path(outdir, f'ok{rank}').write_text(json.dumps({'raised': raised, 'raised3': raised3}))
+    dist.barrier()
+    if comm is not None:
+        comm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,route', [(2, 'peer'), (4, 'peer'), (2, 'collective')])
+def test_metric_session_multi_rank_one_gpu(world, route):
+    out = spawn(_metrics_peer_worker, world, route, timeout=600)
+    for r in range(world):
+        ok = json.loads((out / f'ok{r}').read_text())
+        assert ok['raised'] and ok['raised3'], (r, ok)
