@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument('--grad-wire', choices=['bf16', 'fp32'], default='bf16')
     ap.add_argument('--grad-route', choices=['auto', 'peer', 'nccl'], default='auto')
     ap.add_argument('--metric-route', choices=['auto', 'peer', 'collective'], default='auto')
+    ap.add_argument('--no-graph', action='store_true', help='eager step loop instead of the whole-step CUDA graph')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=3000)
@@ -124,6 +125,7 @@ def native_arm(args):
     if world != args.gpus:
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE is {world}: launch with torchrun --nproc-per-node {args.gpus}')
     K, W = args.steps, max(3, args.warmup)
+    use_graph = not args.no_graph
     torch.backends.cudnn.benchmark = True
 
     def gen_batches(seed, count, pinned):
@@ -150,8 +152,10 @@ def native_arm(args):
                                   nn.Conv2d(16, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(),
                                   nn.Linear(784, 10))  # reference examples/mnist.py:27-36
             self.pipeline.register_model('cnn', model, verbose=False, grad_wire=args.grad_wire)
-            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3))
+            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3,
+                                                                      capturable=use_graph))
             self.loss = nn.CrossEntropyLoss()
+            self.cuda_graph = use_graph  # whole-step CUDA graph after 3 eager steps (graphstep.py)
             self.live_metrics_every = 1  # metrics cross ranks EVERY step (BASELINE configs 2/3)
             self.tracker.deferred = True
             host = gen_batches(100 + rank, W + K, pinned=True)
@@ -171,14 +175,24 @@ def native_arm(args):
                 out = self.pipeline.models['cnn'](x)
             loss = self.loss(out.float(), y)
             self.track_reduce('accuracy', (out.argmax(1) == y).float().mean())
-            if self.read_host and self.live_metrics:  # D2H read of the previous step's reduced metrics
-                self.last_loss = self.live_metrics['train/loss'].value()
-                self.host_reads += 1
             return loss
+
+        def table_columns(self):
+            return [{'name': 'Epoch', 'metric': 'misc/epoch'}, {'name': 'Time/Epoch', 'metric': None},
+                    {'name': 'Loss', 'metric': 'train/loss'}]
+
+        def feed(self, data):
+            """The 'DataLoader': hands out the next batch; in the e2e phase it first reads the previous step's
+            reduced metrics on the host (the D2H result of the per-step exchange), like a progress bar would."""
+            for batch in data:
+                if self.read_host and self.live_metrics:
+                    self.last_loss = self.live_metrics['train/loss'].value()
+                    self.host_reads += 1
+                yield batch
 
         def run_epoch(self):
             phase = self.phases[self.current_epoch - 1]
-            self.pipeline.datasets['train'] = phase.data
+            self.pipeline.datasets['train'] = self.feed(phase.data)
             self.read_host = phase.name == 'e2e'
             sync = self.pipeline.grad_syncs['cnn']
             sync.profile_events = phase.name == 'value'
@@ -230,6 +244,10 @@ def native_arm(args):
     durs = [a.elapsed_time(b) * 1e3 for a, b, _, _ in sync.event_log]  # us
     n_elem = sync.event_log[0][2] if sync.event_log else 0
     route = sync.event_log[0][3] if sync.event_log else None
+    if stage._graph is not None:  # inside the graph no event can be recorded: time the same launches right after
+        durs = stage._graph.time_gradient_sync(100)[10:]
+        n_elem = stage._graph.bucket.total
+        route = 'single' if world == 1 else 'peer'
     per_elem = {('single', 'bf16'): 12, ('single', 'fp32'): 8, ('peer', 'bf16'): 12, ('peer', 'fp32'): 16,
                 ('nccl', 'bf16'): 12, ('nccl', 'fp32'): 8}.get((route, args.grad_wire), 12)
     peaks = load_peaks()
@@ -250,6 +268,8 @@ def native_arm(args):
         'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP, bf16 autocast, Adam, 32 samples/rank/step, '
                                '5 metrics tracked + cross-rank metric exchange every step',
                    'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'grad_wire': args.grad_wire,
+                   'cuda_graph': bool(stage._graph is not None),
+                   'graph_replays': stage._graph.replays if stage._graph is not None else 0,
                    'grad_route': sorted(set(sync.last_routes.values())),
                    'metric_route': 'peer' if pipeline.metric_comm is not None else ('single' if world == 1 else 'collective'),
                    'l2': 'K distinct batches; the whole working set (<10 MB) is L2-resident by the nature of this '
@@ -397,7 +417,7 @@ def cpu_baseline(steps):
     """The reference's CPU path (oracle/ref_port.py) on this box's host cores: bounded sample, W=1."""
     from oracle import ref_port
 
-    cores = os.cpu_count() or 1
+    cores = ref_port.usable_cores()
     res = ref_port.run_baseline(world=1, steps=steps, warmup=50, total_threads=cores, per_step_reduce=True)
     return {'value': round(res['samples_per_s'], 1), 'unit': 'samples/s', 'cores': res['cores'], 'kind': 'port',
             'sample': f'{steps} training steps x 32 samples of the same MNIST-CNN workload (torch CPU, gloo W=1, '
@@ -418,7 +438,7 @@ def reference_arm(args):
     from oracle import ref_port
 
     world = args.gpus
-    cores = os.cpu_count() or 1
+    cores = ref_port.usable_cores()
     res = ref_port.run_baseline(world=world, steps=args.steps, warmup=max(3, args.warmup), total_threads=cores,
                                 per_step_reduce=True)
     value = round(res['samples_per_s'], 1)
@@ -428,7 +448,8 @@ def reference_arm(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP over gloo on host cores, Adam, 32 samples/rank/'
                                'step, metrics reduced across ranks every step (reference CPU path, oracle/ref_port.py)',
-                   'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'threads_per_rank': res['threads_per_rank']},
+                   'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'threads_per_rank': res['threads_per_rank'],
+                   'thread_calibration': res.get('calibration')},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': res['cores'], 'kind': 'port',
                          'sample': f'{args.steps} steps x {BATCH} samples x {world} ranks, {res["seconds"]:.2f} s'},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

@@ -164,6 +164,12 @@ class TrainValStage(Stage):
         self.live_metrics_every = 0
         self.live_metrics = {}
         self.global_step = 0
+        # Extension: capture the whole training step into one CUDA graph after `cuda_graph_warmup` eager
+        # steps and replay it per batch (graphstep.GraphedTrainStep).  Needs static batch shapes, capturable optimizers.
+        self.cuda_graph = False
+        self.cuda_graph_warmup = 3
+        self._graph = None
+        self._eager_steps = 0
 
     # ---- lookups -----------------------------------------------------------------------------------------------------
     def _dataset(self, key):
@@ -224,6 +230,20 @@ class TrainValStage(Stage):
         for opt in self.optimizers():
             opt.step()
 
+    def _graphed_step(self, batch):
+        """True if this batch was consumed by the captured step; False while still warming up eagerly."""
+        if self._graph is None:
+            if self._eager_steps < self.cuda_graph_warmup:
+                self._eager_steps += 1
+                return False
+            from .graphstep import GraphedTrainStep
+
+            self._graph = GraphedTrainStep(self, batch)
+            self._graph.capture(batch)
+            return True
+        self._graph(batch)
+        return True
+
     # ---- epochs ------------------------------------------------------------------------------------------------------
     def run_epoch(self):
         self.train_epoch()
@@ -245,13 +265,16 @@ class TrainValStage(Stage):
 
         for batch in loader:
             began = time.perf_counter_ns()
-            self.zero_grad()
-            loss = self.train_step(batch)
-            self.optimize(loss)
+            in_graph = self._graphed_step(batch) if self.cuda_graph else False
+            if not in_graph:
+                self.zero_grad()
+                loss = self.train_step(batch)
+                self.optimize(loss)
             step_ms = (time.perf_counter_ns() - began) / 1e6  # host time, like the reference (not device-synchronised)
 
-            self.track_reduce(self.loss_metric_name(), loss)
-            self._count_batch('train')
+            if not in_graph:  # (the captured step folds its loss and batch counters itself)
+                self.track_reduce(self.loss_metric_name(), loss)
+                self._count_batch('train')
             self.track_reduce('misc/step_time_ms', step_ms, prefixed=False)
 
             self.global_step += 1

@@ -33,7 +33,7 @@ def batches(seed, steps, batch):
             for _ in range(steps)]
 
 
-def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0):
+def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0, graph=False):
     from dmlcloud_b200 import TrainValStage
     from dmlcloud_b200.pipeline import TrainingPipeline
 
@@ -46,9 +46,10 @@ def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0
             self.pipeline.register_dataset('val', batches(200 + rank, meta['val_steps'], meta['batch']), verbose=False)
             model = make_cnn()
             self.pipeline.register_model('cnn', model, verbose=False)
-            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3))
+            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph))
             self.loss = torch.nn.CrossEntropyLoss()
             self.live_metrics_every = live_every
+            self.cuda_graph = graph
 
         def step(self, batch):
             img, target = batch
@@ -108,7 +109,22 @@ def test_train_w1_matches_reference_run():
         deinitialize_torch_distributed()
 
 
-def _train_worker(rank, world, initfile, outdir, grad_route, metric_route):
+def test_train_w1_cuda_graph_step_matches_reference_run():
+    """The whole-step CUDA graph (3 eager warm-up steps, capture, replays) reproduces the reference run as well."""
+    from dmlcloud_b200.util.distributed import deinitialize_torch_distributed, init_process_group_dummy
+
+    gold = load_json('train_w1.json')
+    init_process_group_dummy()
+    try:
+        p, stage, psum, pabs = run_product(0, gold['meta'], graph=True)
+        compare(p, stage, psum, pabs, gold['ranks'][0])
+        assert stage._graph is not None and stage._graph.replays == gold['meta']['train_steps'] * gold['meta']['epochs'] - 3
+        assert stage._graph.bucket.attached()
+    finally:
+        deinitialize_torch_distributed()
+
+
+def _train_worker(rank, world, initfile, outdir, grad_route, metric_route, graph=False):
     init_gloo(rank, world, initfile)
     import torch.distributed as dist
 
@@ -118,7 +134,7 @@ def _train_worker(rank, world, initfile, outdir, grad_route, metric_route):
     D._here = D.Placement('test', rank, world, 0, world, 0)
     torch.cuda.set_device(0)
     gold = load_json(f'train_w{world}.json')
-    p, stage, psum, pabs = run_product(rank, gold['meta'], grad_route, metric_route)
+    p, stage, psum, pabs = run_product(rank, gold['meta'], grad_route, metric_route, graph=graph)
     compare(p, stage, psum, pabs, gold['ranks'][rank])
     routes = set(p.grad_syncs['cnn'].last_routes.values())
     Path(outdir, f'ok{rank}.json').write_text(json.dumps({'routes': sorted(routes), 'psum': psum}))
@@ -133,3 +149,10 @@ def test_train_w2_peer_path_matches_reference_run():
     res = [json.loads((out / f'ok{r}.json').read_text()) for r in range(2)]
     assert res[0]['routes'] == ['peer'] and res[1]['routes'] == ['peer']
     assert res[0]['psum'] == res[1]['psum']  # replicas stay bit-identical
+
+
+def test_train_w2_cuda_graph_peer_path_matches_reference_run():
+    """W=2 with the captured step: the fused peer all-reduce runs INSIDE the CUDA graph (device-side sequence counter)."""
+    out = spawn(_train_worker, 2, 'peer', 'peer', True, timeout=900)
+    res = [json.loads((out / f'ok{r}.json').read_text()) for r in range(2)]
+    assert res[0]['psum'] == res[1]['psum']
