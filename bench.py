@@ -245,10 +245,10 @@ def native_arm(args):
     n_elem = sync.event_log[0][2] if sync.event_log else 0
     route = sync.event_log[0][3] if sync.event_log else None
     if stage._graph is not None:  # inside the graph no event can be recorded: time the same launches right after
-        durs = stage._graph.time_gradient_sync(100)[10:]
+        durs = stage._graph.time_gradient_sync()[3:]
         n_elem = stage._graph.bucket.total
         route = 'single' if world == 1 else 'peer'
-    per_elem = {('single', 'bf16'): 12, ('single', 'fp32'): 8, ('peer', 'bf16'): 12, ('peer', 'fp32'): 16,
+    per_elem = {('single', 'bf16'): 8, ('single', 'fp32'): 8, ('peer', 'bf16'): 12, ('peer', 'fp32'): 16,
                 ('nccl', 'bf16'): 12, ('nccl', 'fp32'): 8}.get((route, args.grad_wire), 12)
     peaks = load_peaks()
     in_situ = None

@@ -118,6 +118,27 @@ struct UnpackBf16 {  // dst = float(src) * s  (+ sum dst^2)          6 B/elem
     }
 };
 
+template <bool kSumsq>
+struct RoundBf16Inplace {  // buf = float(bf16_rn(buf * s))  (+ sum buf^2)   8 B/elem — the W == 1 form of the bf16 wire
+    typedef float4 In;
+    float *base;
+    float4 *vec;
+    float s;
+    __device__ __forceinline__ static float rt(float f) { return bf16_to_f32(f32_to_bf16(f)); }
+    __device__ __forceinline__ In ld(size_t i) const { return vec[i]; }
+    __device__ __forceinline__ double st(size_t i, In v) const {
+        v.x = rt(v.x * s), v.y = rt(v.y * s), v.z = rt(v.z * s), v.w = rt(v.w * s);
+        vec[i] = v;
+        if (kSumsq) return (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        return 0.0;
+    }
+    __device__ __forceinline__ double scalar(size_t e) const {
+        float f = rt(base[e] * s);
+        base[e] = f;
+        return kSumsq ? (double)f * f : 0.0;
+    }
+};
+
 struct SumsqF32 {  // sum buf^2                                      4 B/elem
     typedef float4 In;
     const float *src;
@@ -277,6 +298,19 @@ int dmlb_bucket_unpack_bf16_f32(const uint16_t *src, float *dst, size_t n, float
     }
     UnpackBf16<false> f{src, dst, reinterpret_cast<const uint2 *>(src + h), reinterpret_cast<float4 *>(dst + h), scale};
     return launch_stream<UnpackBf16<false>, false>(f, head, n, nullptr, (cudaStream_t)stream);
+}
+
+int dmlb_bucket_round_bf16_f32(float *buf, size_t n, float scale, double *sumsq, void *stream) {
+    if (!buf && n) return DMLB_EINVAL;
+    if ((uintptr_t)buf & 3) return DMLB_EALIGN;
+    long head = head_for(buf, 4, 16);
+    float4 *vec = reinterpret_cast<float4 *>(buf + (head > 0 ? head : 0));
+    if (sumsq) {
+        RoundBf16Inplace<true> f{buf, vec, scale};
+        return launch_stream<RoundBf16Inplace<true>, true>(f, head, n, sumsq, (cudaStream_t)stream);
+    }
+    RoundBf16Inplace<false> f{buf, vec, scale};
+    return launch_stream<RoundBf16Inplace<false>, false>(f, head, n, nullptr, (cudaStream_t)stream);
 }
 
 int dmlb_bucket_sumsq_f32(const float *buf, size_t n, double *sumsq, void *stream) {

@@ -192,11 +192,8 @@ class GradBucketSync:
 
         if self.world == 1:
             st = N.stream_ptr()
-            if self.wire == 'bf16':
-                stage = self._stage_for(index, n)
-                N.check(lib.dmlb_bucket_pack_f32_bf16(buf.data_ptr(), stage.data_ptr(), n, self.scale, st), 'pack')
-                N.check(lib.dmlb_bucket_unpack_bf16_f32(stage.data_ptr(), buf.data_ptr(), n, 1.0, sumsq_ptr, st),
-                        'unpack')
+            if self.wire == 'bf16':  # K1 and K2 collapse into one in-place launch when there is nobody to exchange with
+                N.check(lib.dmlb_bucket_round_bf16_f32(buf.data_ptr(), n, self.scale, sumsq_ptr, st), 'round_bf16')
             else:
                 N.check(lib.dmlb_bucket_scale_f32(buf.data_ptr(), n, self.scale, st), 'scale')
                 if sumsq_ptr:

@@ -80,8 +80,6 @@ class GraphedTrainStep:
                                                    not self.comm.fits(self._wire_bytes(self.bucket.total))):
             raise RuntimeError('cuda_graph mode needs the peer-memory communicator (grad_route "auto"/"peer") and a '
                                'gradient set that fits grad_arena_bytes')
-        self.stage_bf16 = torch.empty(self.bucket.total, dtype=torch.bfloat16, device=self.device) \
-            if (self.world == 1 and self.wire == 'bf16') else None
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.static = tuple(torch.empty_like(t, device=self.device) if isinstance(t, torch.Tensor) else t
                             for t in example_batch)
@@ -105,9 +103,7 @@ class GraphedTrainStep:
             N.check(self.lib.dmlb_comm_allreduce(self.comm.handle, flat.data_ptr(), n, WIRES[self.wire],
                                                  1.0 / self.world, sumsq_ptr, 0, st), 'comm_allreduce')
         elif self.wire == 'bf16':
-            N.check(self.lib.dmlb_bucket_pack_f32_bf16(flat.data_ptr(), self.stage_bf16.data_ptr(), n, 1.0, st), 'pack')
-            N.check(self.lib.dmlb_bucket_unpack_bf16_f32(self.stage_bf16.data_ptr(), flat.data_ptr(), n, 1.0,
-                                                         sumsq_ptr, st), 'unpack')
+            N.check(self.lib.dmlb_bucket_round_bf16_f32(flat.data_ptr(), n, 1.0, sumsq_ptr, st), 'round_bf16')
         else:
             N.check(self.lib.dmlb_bucket_scale_f32(flat.data_ptr(), n, 1.0, st), 'scale')
             if clip:
@@ -142,26 +138,44 @@ class GraphedTrainStep:
         self._load(batch)
         if not self.bucket.attached():
             raise RuntimeError('cuda_graph mode: parameter .grad no longer alias the flat bucket')
+        stream = torch.cuda.current_stream(self.device)
+        if stream == torch.cuda.default_stream(self.device):
+            raise RuntimeError('cuda_graph mode must not run on the legacy default stream (TrainingPipeline.run() puts '
+                               'the stages on its compute stream; do the same when driving a stage by hand)')
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the very stream the warm-up steps ran on: autograd's AccumulateGrad nodes (stashed by DDP at
+        # construction) then already live on the capturing stream and no cross-stream edge enters the graph
+        with torch.cuda.graph(self.graph, stream=stream):
             self.loss = self._one_step()
         self.graph.replay()  # capture only records: run the step once for real
         self.replays = 1
         return self.loss
 
-    def time_gradient_sync(self, reps=50):
-        """CUDA-event duration (us) of the gradient-sync launches on the flat bucket, issued eagerly on the current
-        stream — the same launches the graph replays.  Collective: every rank must call it."""
-        times = []
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
+    def time_gradient_sync(self, reps=20, per_graph=20):
+        """Device time (us) of ONE gradient-sync launch on the flat bucket: `per_graph` of them are captured back to
+        back into a throw-away CUDA graph (so host launch latency does not enter) and the replay is timed with CUDA
+        events on the launching stream.  Collective: every rank must call it."""
+        stream = torch.cuda.current_stream(self.device)
+        side = stream if stream != torch.cuda.default_stream(self.device) else torch.cuda.Stream(device=self.device)
+        side.wait_stream(stream)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
             self._sync_gradients()
-            b.record()
-            times.append((a, b))
-        torch.cuda.synchronize(self.device)
-        return [a.elapsed_time(b) * 1e3 for a, b in times]
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(per_graph):
+                    self._sync_gradients()
+            times = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.replay()
+                b.record()
+                times.append((a, b))
+            torch.cuda.synchronize(self.device)
+        stream.wait_stream(side)
+        return [a.elapsed_time(b) * 1e3 / per_graph for a, b in times]
 
     def _load(self, batch):
         for dst, src in zip(self.static, batch):

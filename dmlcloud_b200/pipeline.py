@@ -71,6 +71,7 @@ class TrainingPipeline:
         self.metric_route = 'auto'         # 'auto' | 'peer' | 'collective'
         self.grad_syncs = {}               # model name -> gradsync.GradBucketSync
         self.metric_comm = None
+        self.compute_stream = None         # dedicated stream all stage work runs on (created in run())
         self._save_policy = {}
 
     @property
@@ -192,10 +193,35 @@ class TrainingPipeline:
         """Runs every registered stage; exceptions are logged and the stdout tee / wandb run are closed either way."""
         with _RunGuard(self):
             self._pre_run()
-            for stage in self.stages:
-                self.current_stage = stage
-                stage.run()
+            with self._on_compute_stream():
+                for stage in self.stages:
+                    self.current_stage = stage
+                    stage.run()
             self._post_run()
+
+    def _on_compute_stream(self):
+        """Everything a stage does — DDP construction, the step loop, CUDA-graph capture — runs on ONE dedicated,
+        non-default stream.  The legacy default stream synchronises implicitly with every blocking stream, which both
+        serialises against foreign work and makes whole-step graph capture illegal (autograd's AccumulateGrad nodes
+        remember the stream they were created on)."""
+        import contextlib
+
+        if self.device is None or self.device.type != 'cuda':
+            return contextlib.nullcontext()
+        if self.compute_stream is None:
+            self.compute_stream = torch.cuda.Stream(device=self.device)
+
+        @contextlib.contextmanager
+        def scope():
+            outer = torch.cuda.current_stream(self.device)
+            self.compute_stream.wait_stream(outer)
+            with torch.cuda.stream(self.compute_stream):
+                try:
+                    yield
+                finally:
+                    outer.wait_stream(self.compute_stream)
+
+        return scope()
 
     def _select_device(self):
         if not torch.cuda.is_available():

@@ -85,6 +85,9 @@ int dmlb_bucket_pack_f32_bf16(const float *src, uint16_t *dst, size_t n, float s
 /* dst = float(src) * scale.  If sumsq != NULL, also atomically adds sum(dst^2) (fp64) to *sumsq — the fused first
  * half of clip_grad_norm_ (reference stage.py:276-279), costing no extra HBM pass. */
 int dmlb_bucket_unpack_bf16_f32(const uint16_t *src, float *dst, size_t n, float scale, double *sumsq, void *stream);
+/* buf = float(bf16_rn(buf * scale)) in place (+ optional sum of squares): the bf16 wire at W == 1 — what pack followed by
+ * unpack computes, as one launch and 8 B/elem instead of two launches and 12 B/elem. */
+int dmlb_bucket_round_bf16_f32(float *buf, size_t n, float scale, double *sumsq, void *stream);
 /* sum(buf^2) in fp64 added to *sumsq (fp32-wire counterpart of the fused unpack norm; 4 B/elem) */
 int dmlb_bucket_sumsq_f32(const float *buf, size_t n, double *sumsq, void *stream);
 /* buf *= min(1, max_norm / (sqrt(*sumsq) + 1e-6))  — second half of clip_grad_norm_; reads *sumsq on device, no host sync */

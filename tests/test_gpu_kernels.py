@@ -69,6 +69,16 @@ class TestBucketKernels:
         assert (out[:n].cpu().numpy() == want).all() and (out[n:].cpu().numpy() == -7.0).all()
         np.testing.assert_allclose(sumsq.item(), np.sum(want.astype(np.float64) ** 2), rtol=1e-12)
 
+    @pytest.mark.parametrize('n', SIZES)
+    def test_round_bf16_inplace_equals_pack_then_unpack(self, lib, n):
+        g = rand_grads(n, 77 + n)
+        t = torch.from_numpy(g.copy()).cuda()
+        sumsq = torch.zeros(1, dtype=torch.float64, device='cuda')
+        N_().check(lib.dmlb_bucket_round_bf16_f32(t.data_ptr(), n, 0.25, sumsq.data_ptr(), sptr()))
+        want = grad_oracle.round_bf16(grad_oracle.scale_f32(g, 4))
+        assert (t.cpu().numpy() == want).all()
+        np.testing.assert_allclose(sumsq.item(), np.sum(want.astype(np.float64) ** 2), rtol=1e-12)
+
     @pytest.mark.parametrize('offset', [1, 2, 3])
     def test_misaligned_pointers_take_the_safe_path(self, lib, offset):
         n = 5000
