@@ -358,15 +358,50 @@ def kernel_microbench(dev, peaks):
         'roofline_more': [entry('dmlb_bucket_unpack_bf16_f32 (K2)', 6, n, unpack),
                           entry('dmlb_bucket_scale_f32 (K1, fp32 wire, in place)', 8, n, scale)],
     }
-    # ResNet-18 DDP buckets, L2 flushed by a 512 MB write between launches
-    flush = torch.empty(128 << 20, dtype=torch.float32, device=dev)
+    # ResNet-18 DDP buckets.  A single 10 us launch cannot be timed with an event pair (the pair itself
+    # costs microseconds), so R x [L2 flush, kernel] is captured into a CUDA graph and timed against R x [L2 flush].
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)  # 256 MB write > 126 MB L2
+    side = torch.cuda.Stream(device=dev)
+
+    def graph_time(body, reps=8, R=8):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            body()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(R):
+                    body()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.replay()
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b) * 1e-3 / R)
+        return ts
+
+    def side_ptr():
+        return N.stream_ptr(torch.cuda.current_stream(dev))
+
+    base = statistics.median(graph_time(lambda: flush.zero_()))
     buckets = []
     for elems in (513_000, 7_213_056, 3_963_456, 11_689_512):
         s = src[:elems]
         w = wire[:elems]
-        secs = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(s.data_ptr(), w.data_ptr(), elems, 0.125, st)),
-                     reps=8, warm=2, between=lambda: flush.zero_())
-        buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, secs, 'L2 flushed before each launch'))
+
+        def body():
+            flush.zero_()
+            N.check(lib.dmlb_bucket_pack_f32_bf16(s.data_ptr(), w.data_ptr(), elems, 0.125, side_ptr()))
+
+        secs = [max(t - base, 1e-9) for t in graph_time(body)]
+        buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, secs,
+                             'cold: 256 MB L2 flush before each launch; graph-captured, flush time subtracted'))
+        # the same bucket as the step sees it: just written by backward, i.e. L2-resident
+        warm = graph_time(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(s.data_ptr(), w.data_ptr(), elems, 0.125,
+                                                                         side_ptr())))
+        buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, warm,
+                             'warm: source L2-resident (as right after backward); back-to-back in a graph'))
     out['roofline_resnet18_buckets'] = buckets
     del src, wire, flush
     torch.cuda.empty_cache()
@@ -374,8 +409,10 @@ def kernel_microbench(dev, peaks):
 
 
 def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=200, warm=20):
-    """BASELINE config 5: 1024 scalar metrics; latency from "last value written" to "reduced slab + its D2H copy done",
-    CUDA events on the stream, every rank (max over ranks reported)."""
+    """BASELINE config 5: 1024 scalar metrics (MEAN/SUM/MIN/MAX mix).  Per step: every metric gets a value, then the
+    cross-rank exchange `reduce_live()` runs — ONE fused kernel (finalise + peer exchange + combine) + one D2H copy.
+    Reported: CUDA-event time on the launching stream from "last value folded" to "reduced slab copied to pinned host
+    memory", and the host wall time of the call; max over ranks.  Also the epoch-closing next_epoch()."""
     import torch
     import torch.distributed as dist
 
@@ -389,28 +426,52 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
     for i, name in enumerate(names):
         t.register_metric(name, ops[i % 4])
     vals = torch.randn(n_metrics, generator=torch.Generator().manual_seed(rank)).tolist()
-    lat = []
+    live_us, live_host_us, epoch_us = [], [], []
     for it in range(warm + iters):
         for name, v in zip(names, vals):
             t.track(name, v)  # python floats ride as kernel immediates (31 per fold launch)
         t._slab.flush()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
         a.record()
-        t.next_epoch()  # ONE fused finalise / exchange / combine launch + one D2H copy
+        live = t.reduce_live()
         b.record()
+        h1 = time.perf_counter()
         b.synchronize()
         if it >= warm:
-            lat.append(a.elapsed_time(b) * 1e3)
+            live_us.append(a.elapsed_time(b) * 1e3)
+            live_host_us.append((h1 - h0) * 1e6)
+        if it % 10 == 9:
+            assert live['m1'].value() is not None
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record()
+            t.next_epoch()
+            b2.record()
+            b2.synchronize()
+            epoch_us.append(a2.elapsed_time(b2) * 1e3)
     t._materialize()
-    lat.sort()
-    mine = {'median': lat[len(lat) // 2], 'p99': lat[int(len(lat) * 0.99) - 1], 'min': lat[0]}
+
+    def stats(xs):
+        xs = sorted(xs)
+        return {'median': xs[len(xs) // 2], 'p99': xs[max(0, int(len(xs) * 0.99) - 1)], 'min': xs[0]}
+
+    mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us)}
     box = [None] * world
     dist.all_gather_object(box, mine)
-    return {'n_metrics': n_metrics, 'world': world, 'iters': iters,
-            'median': round(max(b['median'] for b in box), 2), 'p99': round(max(b['p99'] for b in box), 2),
-            'min': round(max(b['min'] for b in box), 2), 'unit': 'us',
-            'what': 'CUDA-event time of MetricTracker.next_epoch(): fused reduce kernel + async D2H of the results'}
+
+    def worst(kind):
+        return {k: round(max(b[kind][k] for b in box), 2) for k in ('median', 'p99', 'min')}
+
+    out = {'n_metrics': n_metrics, 'world': world, 'iters': iters, 'unit': 'us'}
+    out.update(worst('live'))
+    out['host_call'] = worst('host')
+    out['next_epoch'] = worst('epoch')
+    out['what'] = ('median/p99/min: CUDA-event time of MetricTracker.reduce_live() (fused reduce kernel + async D2H of the '
+                   'results) with all 1024 metrics holding a value; host_call: wall time of the Python call; next_epoch: '
+                   'CUDA-event time of the epoch-closing reduce incl. its O(#metrics) host bookkeeping')
+    return out
 
 
 def cpu_baseline(steps):

@@ -564,6 +564,7 @@ class SlabMetric:
         self.dtype = dtype
         slab = self._tracker._slab_or_create()
         self.cell = slab.alloc(self.lanes, _desc_word(self.reduction, dtype, self.globally))
+        self._tracker._version += 1
 
     @property
     def is_int(self):
@@ -673,6 +674,8 @@ class MetricTracker:
         self._comm = None
         self._group = None
         self._has_deferred = False
+        self._version = 0      # bumped whenever the set of reducible cells can have changed
+        self._live_plan = None  # (version, prefix, epoch) -> cached selection of reduce_live
 
     # -- wiring ------------------------------------------------------------------------------------------------------
     def bind(self, device=None, comm=None, group=None, slab=None):
@@ -759,6 +762,7 @@ class MetricTracker:
         if dim is not None and reduction is None:
             raise ValueError('If dim is specified, reduction must be specified as well')
         self._histories[name] = [None] * (self.epoch - 1)
+        self._version += 1
         if reduction is not None:
             self.reducers[name] = SlabMetric(self, name, reduction=reduction, dim=dim, globally=globally)
 
@@ -800,14 +804,18 @@ class MetricTracker:
                 ranges.append([m.cell, m.cell + m.lanes])
         return [tuple(r) for r in ranges]
 
-    def _launch(self, bound, reset):
-        """One reduce launch for the bound (cell-owning) metrics.  Globally-reduced metrics go first and define the
-        cross-rank layout; rank-local metrics (globally=False) follow and are never exchanged."""
-        slab = self._slab_or_create()
+    def _plan(self, bound):
+        """(global ranges, local ranges, layout hash) for a list of cell-owning metrics.  Globally-reduced metrics go
+        first and define the cross-rank layout; rank-local metrics (globally=False) follow and are never exchanged."""
         glob = [m for m in bound if m.globally]
         loc = [m for m in bound if not m.globally]
-        layout = _layout_hash([m.layout_item() for m in glob])
-        return slab.reduce(self._ranges(glob), self._ranges(loc), layout, reset=reset, exchange=True)
+        return self._ranges(glob), self._ranges(loc), _layout_hash([m.layout_item() for m in glob])
+
+    def _launch(self, bound, reset, plan=None):
+        """One reduce launch for the bound (cell-owning) metrics."""
+        slab = self._slab_or_create()
+        g, l, layout = plan if plan is not None else self._plan(bound)
+        return slab.reduce(g, l, layout, reset=reset, exchange=True)
 
     def reduce_all(self, prefix=None, strict=True):
         """Reduces all metrics and appends their reduced values to the history (reference metrics.py:249-273).
@@ -826,6 +834,7 @@ class MetricTracker:
         if bound or (world > 1 and any(m.globally for m in metrics)):
             pending = self._launch(bound, reset=True)
         vote_carrier = None
+        self._version += 1
         for m in metrics:
             if m.cell is None:
                 self._histories[m.name].append(None)
@@ -843,14 +852,20 @@ class MetricTracker:
 
     def reduce_live(self, prefix=None):
         """Cross-rank view of the running values of all (prefix-matching) reduced metrics, WITHOUT closing the epoch:
-        the per-step metric exchange of BASELINE configs 2/3.  Returns {name: handle}; `handle.value()` brings the
-        number to the host (one event sync) when it is actually needed."""
-        metrics = [m for name, m in self.reducers.items()
-                   if (prefix is None or name.startswith(prefix)) and m.cell is not None and not self.has_value(name)]
-        if not metrics:
+        the per-step metric exchange of BASELINE configs 2/3.  Returns a mapping {name: handle}; `handle.value()`
+        brings the number to the host (one event sync) when it is actually needed.  The selection (cell ranges, layout
+        hash) is cached while the metric set is unchanged, so the per-step host cost does not grow with #metrics."""
+        key = (self._version, prefix, self.epoch)
+        if self._live_plan is None or self._live_plan[0] != key:
+            metrics = [m for name, m in self.reducers.items()
+                       if (prefix is None or name.startswith(prefix)) and m.cell is not None
+                       and not self.has_value(name)]
+            self._live_plan = (key, {m.name: m for m in metrics}, self._plan(metrics) if metrics else None)
+        _, by_name, plan = self._live_plan
+        if not by_name:
             return {}
-        pending = self._launch(metrics, reset=False)
-        return {m.name: _Live(pending, m) for m in metrics}
+        pending = self._launch(None, reset=False, plan=plan)
+        return _LiveView(pending, by_name)
 
     def next_epoch(self):
         """Reduces all metrics (if not already reduced) and advances the epoch counter (reference 275-280)."""
@@ -898,3 +913,28 @@ class _Live:
 
     def value(self):
         return MetricTracker._decode(self.pending, self.metric)
+
+
+class _LiveView:
+    """Read-only mapping name -> _Live over one live exchange; handles are made on access (no per-metric work per step)."""
+
+    def __init__(self, pending, by_name):
+        self._pending, self._by_name = pending, by_name
+
+    def __getitem__(self, name):
+        return _Live(self._pending, self._by_name[name])
+
+    def __contains__(self, name):
+        return name in self._by_name
+
+    def __iter__(self):
+        return iter(self._by_name)
+
+    def __len__(self):
+        return len(self._by_name)
+
+    def keys(self):
+        return self._by_name.keys()
+
+    def items(self):
+        return ((name, self[name]) for name in self._by_name)
