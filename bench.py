@@ -277,7 +277,7 @@ def native_arm(args):
         'clocks': value_phase.clocks,
         'e2e': {'value': round(samples / (e2e_ms * 1e-3), 1), 'unit': 'samples/s',
                 'h2d_bytes_per_step': BATCH * (SAMPLE_BYTES_IN + LABEL_BYTES),
-                'd2h_bytes_per_step': 8 + 9 * pipeline.tracker._slab.capacity,
+                'd2h_bytes_per_step': 128 + 9 * pipeline.tracker._slab.capacity,
                 'ms_per_step': round(e2e_ms / K, 4), 'host_reads': stage.host_reads},
         'gpu_launches': value_phase.launches,
         'wall_ms_per_step': round(value_phase.wall_ms / K, 4),
@@ -294,7 +294,7 @@ def native_arm(args):
         result['cpu_baseline'] = cpu_baseline(args.cpu_steps)
     dist.barrier()
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        print(json.dumps(result), file=JSON_OUT, flush=True)
     for s in pipeline.grad_syncs.values():
         s.close()
     if pipeline.metric_comm is not None:
@@ -352,7 +352,14 @@ def kernel_microbench(dev, peaks):
     pack = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
     unpack = timed(lambda: N.check(lib.dmlb_bucket_unpack_bf16_f32(wire.data_ptr(), src.data_ptr(), n, 1.0, None, st)))
     scale = timed(lambda: N.check(lib.dmlb_bucket_scale_f32(src.data_ptr(), n, 1.0, st)))
+    sq = torch.zeros(1, dtype=torch.float64, device=dev)
+    read_only = timed(lambda: N.check(lib.dmlb_bucket_sumsq_f32(src.data_ptr(), n, sq.data_ptr(), st)))
+    write_only = timed(lambda: src.zero_())  # cudaMemset-class fill by torch: context for the write-heavy kernels
     out = {
+        'hbm_context': {'read_only_GBps': round(n * 4 / statistics.mean(read_only) / 1e9, 1),
+                        'write_only_GBps': round(n * 4 / statistics.mean(write_only) / 1e9, 1),
+                        'note': 'read-only = dmlb_bucket_sumsq_f32 (4 B/el); write-only = torch zero_ fill (4 B/el); '
+                                'the measured copy peak is a 50/50 read/write mix'},
         'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, n, pack,
                           'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2)'),
         'roofline_more': [entry('dmlb_bucket_unpack_bf16_f32 (K2)', 6, n, unpack),
@@ -515,11 +522,21 @@ def reference_arm(args):
                          'sample': f'{args.steps} steps x {BATCH} samples x {world} ranks, {res["seconds"]:.2f} s'},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, cuDNN warnings) write to fd 1 too, so
+    fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved original descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
 
 
 if __name__ == '__main__':
     a = parse_args()
+    JSON_OUT = _claim_stdout()
     if a.impl == 'reference':
         reference_arm(a)
     else:

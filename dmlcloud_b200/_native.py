@@ -21,6 +21,7 @@ IPC_HANDLE_BYTES = 64
 MAX_WORLD = 8
 MAX_FOLD_ENTRIES = 32
 MAX_RANGES = 64
+METRIC_STATUS_SLOTS = 32
 
 
 class Seg(Structure):
@@ -46,6 +47,7 @@ SIGNATURES = {
     'dmlb_malloc': (c_int, [POINTER(c_void_p), c_size_t]),
     'dmlb_free': (c_int, [c_void_p]),
     'dmlb_memset_async': (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    'dmlb_host_device_pointer': (c_int, [c_void_p, POINTER(c_void_p)]),
     'dmlb_bucket_scale_f32': (c_int, [c_void_p, c_size_t, c_float, c_void_p]),
     'dmlb_bucket_pack_f32_f32': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
     'dmlb_bucket_pack_f32_bf16': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
@@ -119,6 +121,8 @@ def check(code, where=''):
 def cuda_lib(device_index=None):
     """The library, ready to launch on `device_index` from the calling thread (libdmlb links cudart statically, so the
     current device is per-thread state of ITS runtime: DDP's autograd thread needs its own dmlb_set_device)."""
+    if device_index is not None and _lib is not None and getattr(_tls, 'device', None) == device_index:
+        return _lib  # hot path: this thread already selected that device in libdmlb's runtime
     import torch
 
     if not torch.cuda.is_available():

@@ -172,6 +172,12 @@ int dmlb_memset_async(void *ptr, int value, size_t bytes, void *stream) {
     return DMLB_OK;
 }
 
+int dmlb_host_device_pointer(void *host, void **device) {
+    if (!host || !device) return DMLB_EINVAL;
+    DMLB_CUDA(cudaHostGetDevicePointer(device, host, 0));
+    return DMLB_OK;
+}
+
 int dmlb_ipc_get_handle(void *ptr, unsigned char handle[DMLB_IPC_HANDLE_BYTES]) {
     cudaIpcMemHandle_t h;
     DMLB_CUDA(cudaIpcGetMemHandle(&h, ptr));

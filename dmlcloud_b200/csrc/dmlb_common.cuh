@@ -98,13 +98,18 @@ __device__ __forceinline__ double block_sum(double v) {
     return t;
 }
 
-// grid for a streaming kernel over `nvec` vector items, `per_thread` items per thread per sweep
+// Grid for a grid-stride streaming kernel over `nvec` vector items, `per_thread` items per thread per sweep.
+// Small inputs: one CTA per sweep-chunk.  Large inputs: at most sm_count * ctas_per_sm resident CTAs, and the count is
+// chosen so that the number of sweeps is (almost) an integer — a plain "min(want, cap)" leaves the last sweep
+// partially filled, i.e. some SMs idle for up to one sweep (1.49 sweeps -> 75 % efficiency at a 27 MiB bucket).
 inline int stream_grid(size_t nvec, int per_thread, int ctas_per_sm) {
     size_t per_cta = (size_t)kThreads * per_thread;
     size_t want = (nvec + per_cta - 1) / per_cta;
     size_t cap = (size_t)sm_count() * ctas_per_sm;
     if (want < 1) want = 1;
-    return (int)(want < cap ? want : cap);
+    if (want <= cap) return (int)want;
+    size_t sweeps = (want + cap - 1) / cap;
+    return (int)((want + sweeps - 1) / sweeps);
 }
 
 }  // namespace dmlb

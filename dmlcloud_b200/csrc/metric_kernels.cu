@@ -276,7 +276,10 @@ metric_reduce_kernel(const __grid_constant__ CommDev c, bool has_comm, uint64_t 
             out_flag[cell] = n > 0 ? 0 : 1;
         }
     }
-    if (!exchange) return;
+    if (!exchange) {
+        if (threadIdx.x == 0) status[blockIdx.x] = DMLB_METRIC_OK;
+        return;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         rec_mine[0] = layout_hash;
         rec_mine[1] = (uint64_t)n_sel;
@@ -307,7 +310,10 @@ metric_reduce_kernel(const __grid_constant__ CommDev c, bool has_comm, uint64_t 
         out_val[cell] = out;
         out_flag[cell] = flag;
     }
-    if (st != DMLB_METRIC_OK) atomicMax(status, st);
+    // one status slot per CTA (DMLB_METRIC_STATUS_SLOTS of them): no memset before the launch, no atomics
+    st = __syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE) ? DMLB_METRIC_SPLIT_VOTE
+                                                         : (__syncthreads_or(st == DMLB_METRIC_LAYOUT) ? DMLB_METRIC_LAYOUT : DMLB_METRIC_OK);
+    if (threadIdx.x == 0) status[blockIdx.x] = st;
     comm_end(c, s);
 }
 
@@ -358,7 +364,9 @@ metric_combine_kernel(const uint64_t *__restrict__ gathered, int world, int rank
         out_val[cell] = out;
         out_flag[cell] = flag;
     }
-    if (st != DMLB_METRIC_OK) atomicMax(status, st);
+    st = __syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE) ? DMLB_METRIC_SPLIT_VOTE
+                                                         : (__syncthreads_or(st == DMLB_METRIC_LAYOUT) ? DMLB_METRIC_LAYOUT : DMLB_METRIC_OK);
+    if (threadIdx.x == 0) status[blockIdx.x] = st;
 }
 
 static int fill_ranges(RangeParams &R, const dmlb_range *ranges, int n_ranges, int n_cells, int &n_sel) {
@@ -424,7 +432,7 @@ int dmlb_metric_reduce(void *comm, uint64_t *acc, int64_t *cnt, const uint32_t *
         dev.world = 1;
     }
     int grid = (n_sel + kCommThreads - 1) / kCommThreads;
-    if (grid > 32) grid = 32;
+    if (grid > DMLB_METRIC_STATUS_SLOTS) grid = DMLB_METRIC_STATUS_SLOTS;
     if (grid < 1) grid = 1;
     metric_reduce_kernel<<<grid, kCommThreads, 0, (cudaStream_t)stream>>>(dev, has, acc, (long long *)cnt, desc, R, n_sel,
                                                                            layout_hash, reset != 0, out_val, out_flag, status);
@@ -457,7 +465,7 @@ int dmlb_metric_combine(const uint64_t *gathered, int world, int rank, const uin
     if (rc != DMLB_OK) return rc;
     if (n_sel == 0) return DMLB_OK;
     int grid = (n_sel + kCommThreads - 1) / kCommThreads;
-    grid = grid > 32 ? 32 : grid;
+    grid = grid > DMLB_METRIC_STATUS_SLOTS ? DMLB_METRIC_STATUS_SLOTS : grid;
     metric_combine_kernel<<<grid, kCommThreads, 0, (cudaStream_t)stream>>>(gathered, world, rank, desc, R, n_sel, out_val,
                                                                             out_flag, status);
     return launched();

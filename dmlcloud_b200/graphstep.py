@@ -142,6 +142,9 @@ class GraphedTrainStep:
         if stream == torch.cuda.default_stream(self.device):
             raise RuntimeError('cuda_graph mode must not run on the legacy default stream (TrainingPipeline.run() puts '
                                'the stages on its compute stream; do the same when driving a stage by hand)')
+        # host scalars queued by the last eager step must be launched NOW: flushed inside the capture they would be
+        # baked into the graph and re-added by every replay
+        self.stage.tracker._slab_or_create().flush()
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         # capture on the very stream the warm-up steps ran on: autograd's AccumulateGrad nodes (stashed by DDP at

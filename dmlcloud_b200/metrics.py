@@ -114,32 +114,38 @@ def _world(group=None):
 # ----------------------------------------------------------------------------------------------------------------------
 # device slab
 # ----------------------------------------------------------------------------------------------------------------------
+STATUS_BYTES = 4 * N.METRIC_STATUS_SLOTS  # one int32 status slot per CTA of a reduce launch
+
+
 class _PendingResult:
-    """Results of one reduce launch on their way to the host (async D2H + event)."""
+    """Results of one reduce launch on their way to the host: the kernel writes them straight into mapped pinned host
+    memory (or they are copied there), and an event marks completion."""
 
     def __init__(self, slab, host, event, capacity):
         self.slab, self.host, self.event, self.capacity = slab, host, event, capacity
         self._parsed = None
 
     def ready(self):
-        return self.event.query()
+        return self._parsed is not None or self.event.query()
 
     def get(self):
         if self._parsed is None:
             self.event.synchronize()
             cap = self.capacity
-            status = int(self.host[:4].view(torch.int32)[0])
-            vals = self.host[8:8 + 8 * cap].view(torch.int64).clone()
-            flags = self.host[8 + 8 * cap:8 + 9 * cap].clone()
-            self.slab._release_host(self.host)
-            self.host = None
+            status = int(self.host[:STATUS_BYTES].view(torch.int32).max())
+            vals = self.host[STATUS_BYTES:STATUS_BYTES + 8 * cap].view(torch.int64).clone()
+            flags = self.host[STATUS_BYTES + 8 * cap:STATUS_BYTES + 9 * cap].clone()
+            self.slab._release_host(self.host, self.event)
+            self.host = self.event = None
             self._parsed = (status, vals, flags)
         return self._parsed
 
 
 class DeviceSlab:
-    """HBM layout: acc u64[C] | cnt i64[C] | desc u32[C]  +  out = status(8 B) | val u64[C] | flag u8[C].
-    One instance per tracker; every launch goes on the caller's current stream."""
+    """HBM layout: acc u64[C] | cnt i64[C] | desc u32[C]  +  out = status(32 x i32) | val u64[C] | flag u8[C].
+    Results destined for the host are written by the reduce kernel directly into device-mapped pinned host memory
+    (same layout), so a reduce is ONE launch + one event record.  One instance per tracker; every launch goes on the
+    caller's current stream."""
 
     GROW = 1024
 
@@ -161,6 +167,10 @@ class DeviceSlab:
         self.n_cells = 0
         self.acc = self.cnt = self.desc = self.out = None
         self._host_pool = []
+        self._event_pool = []
+        self._host_dptr = {}
+        self._range_cache = {}
+        self._host_mapped = None  # None = not probed yet; False = pinned memory is not device-mapped here (copy path)
         self._imm = []
         self._imm_cells = set()
         self._grow(self.GROW)
@@ -176,7 +186,7 @@ class DeviceSlab:
             for k, t in new.items():
                 t[:self.capacity].copy_(getattr(self, k))
         self.acc, self.cnt, self.desc = new['acc'], new['cnt'], new['desc']
-        self.out = torch.zeros(8 + 9 * capacity, dtype=torch.uint8, device=self.device)
+        self.out = torch.zeros(STATUS_BYTES + 9 * capacity, dtype=torch.uint8, device=self.device)
         self.capacity = capacity
         self._host_pool = []
 
@@ -205,16 +215,33 @@ class DeviceSlab:
         self.n_cells = n_cells
 
     def _acquire_host(self):
-        size = 8 + 9 * self.capacity
+        """(pinned host block, device address of it or None).  Blocks are pooled; status slots are zero on hand-out."""
+        size = STATUS_BYTES + 9 * self.capacity
         while self._host_pool:
-            h = self._host_pool.pop()
-            if h.numel() == size:
-                return h
-        return torch.empty(size, dtype=torch.uint8, pin_memory=True)
+            host, dptr = self._host_pool.pop()
+            if host.numel() == size:
+                return host, dptr
+        host = torch.zeros(size, dtype=torch.uint8, pin_memory=True)
+        dptr = None
+        if self._host_mapped is not False:
+            out = ctypes.c_void_p()
+            rc = self._lib().dmlb_host_device_pointer(host.data_ptr(), ctypes.byref(out))
+            self._host_mapped = rc == N.OK and bool(out.value)
+            dptr = out.value if self._host_mapped else None
+        self._host_dptr[host.data_ptr()] = dptr
+        return host, dptr
 
-    def _release_host(self, host):
-        if host.numel() == 8 + 9 * self.capacity and len(self._host_pool) < 16:
-            self._host_pool.append(host)
+    def _release_host(self, host, event=None):
+        if event is not None and len(self._event_pool) < 64:
+            self._event_pool.append(event)
+        if host.numel() == STATUS_BYTES + 9 * self.capacity and len(self._host_pool) < 16:
+            host[:STATUS_BYTES].zero_()
+            self._host_pool.append((host, self._host_dptr.get(host.data_ptr())))
+        else:
+            self._host_dptr.pop(host.data_ptr(), None)
+
+    def _event(self):
+        return self._event_pool.pop() if self._event_pool else torch.cuda.Event()
 
     # -- fold --------------------------------------------------------------------------------------------------------
     def fold_imm(self, cell, value, is_int):
@@ -249,6 +276,17 @@ class DeviceSlab:
                                              len(entries), N.stream_ptr()), 'metric_fold')
 
     # -- reduce ------------------------------------------------------------------------------------------------------
+    def _range_array(self, ranges):
+        key = tuple(ranges)
+        hit = self._range_cache.get(key)
+        if hit is None:
+            if len(self._range_cache) > 64:
+                self._range_cache.clear()
+            chunks = [key[i:i + N.MAX_RANGES] for i in range(0, len(key), N.MAX_RANGES)] or [()]
+            hit = [((N.Range * max(len(c), 1))(*[N.Range(b, e) for b, e in c]), len(c)) for c in chunks]
+            self._range_cache[key] = hit
+        return hit
+
     def reduce(self, global_ranges, local_ranges, layout_hash, reset=True, exchange=True, to_host=True):
         """Finalise + cross-rank combine.  `global_ranges` are the cells of globally-reduced metrics (identical layout
         on every rank, covered by `layout_hash`, exchanged); `local_ranges` are rank-local metrics (never exchanged,
@@ -259,21 +297,21 @@ class DeviceSlab:
         if not exchange:
             world = 1
         st = N.stream_ptr()
-        out = self.out
-        status_ptr = out.data_ptr()
-        val_ptr = out.data_ptr() + 8
-        flag_ptr = out.data_ptr() + 8 + 8 * self.capacity
-        N.check(lib.dmlb_memset_async(status_ptr, 0, 8, st), 'memset')
+        host = None
+        base = self.out.data_ptr()
+        if to_host:
+            host, dptr = self._acquire_host()
+            if dptr is not None:
+                base = dptr  # the kernel writes its results straight into mapped pinned host memory
+        status_ptr, val_ptr, flag_ptr = base, base + STATUS_BYTES, base + STATUS_BYTES + 8 * self.capacity
 
         def launch(comm_handle, ranges):
             # > DMLB_MAX_RANGES fragments (pathological prefix selections) take several launches
-            chunks = [ranges[i:i + N.MAX_RANGES] for i in range(0, len(ranges), N.MAX_RANGES)] or [[]]
-            for chunk in chunks:
-                if not chunk and comm_handle is None:
+            for arr, n in self._range_array(ranges):
+                if n == 0 and comm_handle is None:
                     continue
-                arr = (N.Range * max(len(chunk), 1))(*[N.Range(b, e) for b, e in chunk])
                 N.check(lib.dmlb_metric_reduce(comm_handle, self.acc.data_ptr(), self.cnt.data_ptr(),
-                                               self.desc.data_ptr(), self.n_cells, arr, len(chunk), layout_hash,
+                                               self.desc.data_ptr(), self.n_cells, arr, n, layout_hash,
                                                int(reset), val_ptr, flag_ptr, status_ptr, st), 'metric_reduce')
 
         if world == 1:
@@ -288,9 +326,9 @@ class DeviceSlab:
                                         status_ptr, st)
         if not to_host:
             return None
-        host = self._acquire_host()
-        host.copy_(out, non_blocking=True)
-        event = torch.cuda.Event()
+        if base == self.out.data_ptr():  # pinned memory not device-mapped on this platform: one D2H copy instead
+            host.copy_(self.out, non_blocking=True)
+        event = self._event()
         event.record()
         return _PendingResult(self, host, event, self.capacity)
 
@@ -326,7 +364,7 @@ class DeviceSlab:
 
     def result_view(self, cell, lanes, is_int):
         """Device view of the last reduce's values for cells [cell, cell+lanes) (no host sync)."""
-        vals = self.out[8:8 + 8 * self.capacity].view(torch.int64 if is_int else torch.float64)
+        vals = self.out[STATUS_BYTES:STATUS_BYTES + 8 * self.capacity].view(torch.int64 if is_int else torch.float64)
         return vals[cell:cell + lanes]
 
     # -- checkpoint --------------------------------------------------------------------------------------------------
@@ -394,7 +432,7 @@ def _device_reduce(stacked, reduction, dims, steps_axis, group=None, globally=Fa
     slab.reduce(rng if globally else [], [] if globally else rng, layout, reset=True, exchange=globally, to_host=False)
     is_int = not _is_float(dtype)
     result = slab.result_view(cell, lanes, is_int).to(out_dtype).reshape(residual)
-    status = slab.out[:4].view(torch.int32)
+    status = slab.out[:STATUS_BYTES].view(torch.int32).max().reshape(1)
     slab.release_to(mark)
     return result, status
 

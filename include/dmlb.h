@@ -69,6 +69,8 @@ uint64_t dmlb_launch_count(void);
 int dmlb_malloc(void **ptr, size_t bytes);
 int dmlb_free(void *ptr);
 int dmlb_memset_async(void *ptr, int value, size_t bytes, void *stream);
+/* device address of a pinned (cudaHostAlloc'd / registered) host pointer, or an error if it is not device-mapped */
+int dmlb_host_device_pointer(void *host, void **device);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K1 / K2 — gradient-bucket scale + cast (single GPU, HBM-bound elementwise)                                         */
@@ -169,7 +171,9 @@ typedef struct {
     int32_t begin, end; /* cell range [begin, end) selected for this reduce */
 } dmlb_range;
 #define DMLB_MAX_RANGES 64
-/* status word written by dmlb_metric_reduce */
+/* status: DMLB_METRIC_STATUS_SLOTS int32 slots; every CTA of a reduce / combine launch writes its own slot (slot i < grid),
+ * the caller zero-fills the block once at allocation and takes the maximum — no memset per launch, no atomics. */
+#define DMLB_METRIC_STATUS_SLOTS 32
 #define DMLB_METRIC_OK 0
 #define DMLB_METRIC_SPLIT_VOTE 1 /* some ranks tracked values and some did not (metrics.py:127-128) */
 #define DMLB_METRIC_LAYOUT 2     /* ranks disagree on the slab layout                                */
@@ -178,7 +182,8 @@ typedef struct {
  * the per-step "live" exchange: every rank sees the running global value, the epoch keeps accumulating.
  *   out_val[c]  : 8 bytes — a double (float kinds; already rounded to fp32 when the metric is fp32) or an int64
  *   out_flag[c] : 0 value present, 1 empty (history entry is None)
- *   status      : one int32, DMLB_METRIC_*
+ *   status      : DMLB_METRIC_STATUS_SLOTS int32 (see above), each DMLB_METRIC_*; out_val / out_flag / status may point
+ *                 into device-mapped pinned host memory (results then need no D2H copy)
  * comm may be NULL when world == 1.  layout_hash must be equal on all ranks. */
 int dmlb_metric_reduce(void *comm, uint64_t *acc, int64_t *cnt, const uint32_t *desc, int n_cells,
                        const dmlb_range *ranges, int n_ranges, uint64_t layout_hash, int reset, uint64_t *out_val,

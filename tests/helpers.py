@@ -84,3 +84,10 @@ def init_gloo(rank, world, initfile):
     sys.path.insert(0, str(REPO / 'tests'))
     torch.set_num_threads(1)
     dist.init_process_group('gloo', init_method=f'file://{initfile}', rank=rank, world_size=world)
+
+
+def rank_device(rank):
+    """CUDA device index for a test rank: distinct GPUs when the box has several (real NVLink peers), cuda:0 shared by
+    all ranks on a one-GPU box (peer mappings then go through CUDA IPC on the same device)."""
+    n = torch.cuda.device_count()
+    return rank % n if n > 0 else 0

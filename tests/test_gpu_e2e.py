@@ -131,8 +131,10 @@ def _train_worker(rank, world, initfile, outdir, grad_route, metric_route, graph
     from dmlcloud_b200.util import distributed as D
 
     # all ranks share cuda:0 (one-GPU CI box): placement says local_rank 0 for everybody
-    D._here = D.Placement('test', rank, world, 0, world, 0)
-    torch.cuda.set_device(0)
+    from helpers import rank_device
+
+    D._here = D.Placement('test', rank, world, rank_device(rank), world, 0)
+    torch.cuda.set_device(rank_device(rank))
     gold = load_json(f'train_w{world}.json')
     p, stage, psum, pabs = run_product(rank, gold['meta'], grad_route, metric_route, graph=graph)
     compare(p, stage, psum, pabs, gold['ranks'][rank])

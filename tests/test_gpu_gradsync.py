@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from conftest import load_npz
-from helpers import init_gloo, spawn
+from helpers import init_gloo, rank_device, spawn
 from oracle import grad_oracle
 
 pytestmark = pytest.mark.gpu
@@ -95,11 +95,14 @@ def _allreduce_worker(rank, world, initfile, outdir, cases):
     from dmlcloud_b200 import _native as N
     from dmlcloud_b200.gradsync import WIRES, GradBucketSync
 
-    torch.cuda.set_device(0)
+    from helpers import rank_device
+
+    di = rank_device(rank)
+    torch.cuda.set_device(di)
     results = {}
-    syncs = {w: GradBucketSync('cuda:0', wire=w, route='peer', max_message_bytes=8 << 20, track_sumsq=True)
+    syncs = {w: GradBucketSync(f'cuda:{di}', wire=w, route='peer', max_message_bytes=8 << 20, track_sumsq=True)
              for w in ('fp32', 'bf16')}
-    lib = N.cuda_lib(0)
+    lib = N.cuda_lib(di)
     for name, wire, algo, source in cases:
         if source.startswith('golden:'):
             z = np.load(Path(__file__).parent / 'golden' / source[7:])

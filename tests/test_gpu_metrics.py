@@ -233,8 +233,10 @@ def _metrics_peer_worker(rank, world, initfile, outdir, route):
     from dmlcloud_b200.gradsync import PeerComm
     from dmlcloud_b200.metrics import MetricTracker, Reduction
 
-    torch.cuda.set_device(0)
-    dev = torch.device('cuda', 0)
+    from helpers import rank_device
+
+    torch.cuda.set_device(rank_device(rank))
+    dev = torch.device('cuda', rank_device(rank))
     comm = PeerComm(dev, None, max_message_bytes=1 << 20) if route == 'peer' else None
     gold = load_json(f'metrics_w{world}.json')
     t = MetricTracker()
