@@ -34,8 +34,20 @@ int sm_count() {
     return cached[dev];
 }
 
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 4;      // independent vector loads a thread issues before its first store
 constexpr int kCtasPerSm = 4;
+
+// Each functor says how many elements one of its vector items covers (4: one 128-bit fp32 access; 8: one 128-bit bf16
+// access = two 128-bit fp32 accesses).
+template <class F>
+struct elems_of {
+    static constexpr int value = 4;
+};
+// ... and how many items a thread keeps in flight (register budget: 32 regs/thread for 4 CTAs x 512 threads per SM)
+template <class F>
+struct unroll_of {
+    static constexpr int value = kUnroll;
+};
 
 // ---- functors: In = what one vector load returns, ld/st on vector index, scalar fallbacks on element index ---------
 struct ScaleInplace {  // buf *= s                                   8 B/elem
@@ -118,6 +130,69 @@ struct UnpackBf16 {  // dst = float(src) * s  (+ sum dst^2)          6 B/elem
     }
 };
 
+// 8 elements per item: the bf16 side moves 128 bits per access too (half as many LSU instructions as the x4 forms)
+struct PackBf16x8 {  // dst = bf16_rn(src * s)                       6 B/elem
+    struct In {
+        float4 a, b;
+    };
+    const float *src;
+    uint16_t *dst;
+    const float4 *vsrc;
+    uint4 *vdst;
+    float s;
+    __device__ __forceinline__ In ld(size_t i) const { return In{ld_stream_f4(vsrc + 2 * i), ld_stream_f4(vsrc + 2 * i + 1)}; }
+    __device__ __forceinline__ double st(size_t i, In v) const {
+        uint4 o;
+        o.x = pack_bf16x2(v.a.x * s, v.a.y * s), o.y = pack_bf16x2(v.a.z * s, v.a.w * s);
+        o.z = pack_bf16x2(v.b.x * s, v.b.y * s), o.w = pack_bf16x2(v.b.z * s, v.b.w * s);
+        vdst[i] = o;
+        return 0.0;
+    }
+    __device__ __forceinline__ double scalar(size_t e) const {
+        dst[e] = f32_to_bf16(src[e] * s);
+        return 0.0;
+    }
+};
+template <>
+struct elems_of<PackBf16x8> {
+    static constexpr int value = 8;
+};
+template <>
+struct unroll_of<PackBf16x8> {
+    static constexpr int value = 2;  // 2 items = 4 x LDG.128 in flight, same bytes as the x4 form, no spills
+};
+
+template <bool kSumsq>
+struct UnpackBf16x8 {  // dst = float(src) * s  (+ sum dst^2)        6 B/elem
+    typedef uint4 In;
+    const uint16_t *src;
+    float *dst;
+    const uint4 *vsrc;
+    float4 *vdst;
+    float s;
+    __device__ __forceinline__ In ld(size_t i) const { return ld_stream_u4(vsrc + i); }
+    __device__ __forceinline__ double st(size_t i, In v) const {
+        float4 p, q;
+        p.x = bf16_lo(v.x) * s, p.y = bf16_hi(v.x) * s, p.z = bf16_lo(v.y) * s, p.w = bf16_hi(v.y) * s;
+        q.x = bf16_lo(v.z) * s, q.y = bf16_hi(v.z) * s, q.z = bf16_lo(v.w) * s, q.w = bf16_hi(v.w) * s;
+        vdst[2 * i] = p;
+        vdst[2 * i + 1] = q;
+        if (kSumsq)
+            return (double)p.x * p.x + (double)p.y * p.y + (double)p.z * p.z + (double)p.w * p.w +
+                   (double)q.x * q.x + (double)q.y * q.y + (double)q.z * q.z + (double)q.w * q.w;
+        return 0.0;
+    }
+    __device__ __forceinline__ double scalar(size_t e) const {
+        float f = bf16_to_f32(src[e]) * s;
+        dst[e] = f;
+        return kSumsq ? (double)f * f : 0.0;
+    }
+};
+template <bool kSumsq>
+struct elems_of<UnpackBf16x8<kSumsq>> {
+    static constexpr int value = 8;
+};
+
 template <bool kSumsq>
 struct RoundBf16Inplace {  // buf = float(bf16_rn(buf * s))  (+ sum buf^2)   8 B/elem — the W == 1 form of the bf16 wire
     typedef float4 In;
@@ -185,26 +260,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 stream_kernel(F f, size_t head, size_t nvec, size_t n, double *sumsq_out) {
     prologue(f);
     double part = 0.0;
-    const size_t sweep = (size_t)gridDim.x * kThreads * kUnroll;
-    for (size_t base = (size_t)blockIdx.x * kThreads * kUnroll + threadIdx.x; base < nvec; base += sweep) {
-        typename F::In v[kUnroll];
+    constexpr int U = unroll_of<F>::value;
+    const size_t sweep = (size_t)gridDim.x * kThreads * U;
+    for (size_t base = (size_t)blockIdx.x * kThreads * U + threadIdx.x; base < nvec; base += sweep) {
+        typename F::In v[U];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
             size_t i = base + (size_t)u * kThreads;
             if (i < nvec) v[u] = f.ld(i);
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
             size_t i = base + (size_t)u * kThreads;
             if (i < nvec) part += f.st(i, v[u]);
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x < 8) {  // unaligned head (< 4 elems) and tail (< 4 elems)
+    if (blockIdx.x == 0 && threadIdx.x < 16) {  // unaligned head (< 4 elems) and ragged tail (< kElems elems)
         size_t t = threadIdx.x;
-        if (t < 4) {
+        if (t < 8) {
             if (t < head) part += f.scalar(t);
         } else {
-            size_t e = head + nvec * 4 + (t - 4);
+            size_t e = head + nvec * elems_of<F>::value + (t - 8);
             if (e < n) part += f.scalar(e);
         }
     }
@@ -245,8 +321,8 @@ static int launch_stream(F f, long head, size_t n, double *sumsq, cudaStream_t s
         return launched();
     }
     size_t h = (size_t)head < n ? (size_t)head : n;
-    size_t nvec = (n - h) / 4;
-    int grid = stream_grid(nvec, kUnroll, kCtasPerSm);
+    size_t nvec = (n - h) / elems_of<F>::value;
+    int grid = stream_grid(nvec, unroll_of<F>::value, kCtasPerSm);
     stream_kernel<F, kReduce><<<grid, kThreads, 0, st>>>(f, h, nvec, n, sumsq);
     return launched();
 }
@@ -281,6 +357,10 @@ int dmlb_bucket_pack_f32_bf16(const float *src, uint16_t *dst, size_t n, float s
     long head = head_for(src, 4, 16);
     if (head >= 0 && (((uintptr_t)(dst + head)) & 7)) head = -1;
     size_t h = head > 0 ? head : 0;
+    if (head >= 0 && (((uintptr_t)(dst + h)) & 15) == 0) {  // both sides 16-byte aligned: 128-bit accesses on the bf16 side too
+        PackBf16x8 f8{src, dst, reinterpret_cast<const float4 *>(src + h), reinterpret_cast<uint4 *>(dst + h), scale};
+        return launch_stream<PackBf16x8, false>(f8, head, n, nullptr, (cudaStream_t)stream);
+    }
     PackBf16 f{src, dst, reinterpret_cast<const float4 *>(src + h), reinterpret_cast<uint2 *>(dst + h), scale};
     return launch_stream<PackBf16, false>(f, head, n, nullptr, (cudaStream_t)stream);
 }
@@ -291,6 +371,16 @@ int dmlb_bucket_unpack_bf16_f32(const uint16_t *src, float *dst, size_t n, float
     long head = head_for(dst, 4, 16);
     if (head >= 0 && (((uintptr_t)(src + head)) & 7)) head = -1;
     size_t h = head > 0 ? head : 0;
+    if (head >= 0 && (((uintptr_t)(src + h)) & 15) == 0) {  // 128-bit loads on the bf16 side
+        const uint4 *vs = reinterpret_cast<const uint4 *>(src + h);
+        float4 *vd = reinterpret_cast<float4 *>(dst + h);
+        if (sumsq) {
+            UnpackBf16x8<true> f8{src, dst, vs, vd, scale};
+            return launch_stream<UnpackBf16x8<true>, true>(f8, head, n, sumsq, (cudaStream_t)stream);
+        }
+        UnpackBf16x8<false> f8{src, dst, vs, vd, scale};
+        return launch_stream<UnpackBf16x8<false>, false>(f8, head, n, nullptr, (cudaStream_t)stream);
+    }
     if (sumsq) {
         UnpackBf16<true> f{src, dst, reinterpret_cast<const uint2 *>(src + h), reinterpret_cast<float4 *>(dst + h),
                            scale};
