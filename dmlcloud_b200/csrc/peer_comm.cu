@@ -93,11 +93,72 @@ __device__ __forceinline__ double store_bucket(float *bucket, size_t g, size_t n
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Memory-level parallelism.  A peer load over NVLink takes ~2-3 us; to keep 770 GB/s busy ~2 MB must be in flight per
+// GPU.  With <= 296 x 256 threads that means several independent 16-byte loads per thread: every loop below gathers
+// kU vectors x W ranks into registers before the first add (kU = 4 for W <= 2, 2 for W <= 4, 1 for W <= 8 keeps the
+// register budget at ~32 data registers).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int kWire, int kU>
+__device__ __forceinline__ double pack_range(const CommDev &c, const float *bucket, uint4 *mine, size_t lo, size_t hi,
+                                             size_t n, float scale) {
+    typedef Wire<kWire> W;
+    constexpr int E = W::kElems;
+    for (size_t g0 = lo + threadIdx.x; g0 < hi; g0 += (size_t)kCommThreads * kU) {
+        float v[kU][E];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t g = g0 + (size_t)u * kCommThreads;
+            if (g < hi) load_bucket<E>(bucket, g, n, scale, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t g = g0 + (size_t)u * kCommThreads;
+            if (g < hi) mine[g] = W::pack(v[u]);
+        }
+    }
+    return 0.0;
+}
+
+// out(g) = sum over ranks of stage[r][g] for g in [lo, hi) (index space of the staging buffers, offset `goff`)
+template <int kWire, int kU, class Sink>
+__device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t lo, size_t hi, size_t goff, Sink sink) {
+    typedef Wire<kWire> W;
+    constexpr int E = W::kElems;
+    constexpr int kMaxW = DMLB_MAX_WORLD / kU;  // the host picks kU so that world <= kMaxW: kU x kMaxW = 8 vectors in flight
+    for (size_t i0 = lo + threadIdx.x; i0 < hi; i0 += (size_t)kCommThreads * kU) {
+        uint4 w[kU][kMaxW];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t i = i0 + (size_t)u * kCommThreads;
+            if (i < hi) {
+#pragma unroll
+                for (int r = 0; r < kMaxW; ++r)
+                    if (r < c.world) w[u][r] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.stage(r, half)) + goff + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t i = i0 + (size_t)u * kCommThreads;
+            if (i < hi) {
+                float acc[E];
+#pragma unroll
+                for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+#pragma unroll
+                for (int r = 0; r < kMaxW; ++r)
+                    if (r < c.world) W::accumulate(acc, w[u][r]);
+                sink(i, acc);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // one-shot
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kWire>
+template <int kWire, int kU>
 __global__ void __launch_bounds__(kCommThreads, 2)
-allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, float scale, double *sumsq_out) {
+allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, float scale,
+                         double *sumsq_out) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
     const uint32_t s = comm_begin(c);
@@ -106,28 +167,14 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     const size_t lo = (size_t)blockIdx.x * per;
     const size_t hi = min(nvec, lo + per);
 
-    uint4 *mine = reinterpret_cast<uint4 *>(c.stage(c.rank, half));
-    for (size_t g = lo + threadIdx.x; g < hi; g += kCommThreads) {
-        float v[E];
-        load_bucket<E>(bucket, g, n, scale, v);
-        mine[g] = W::pack(v);
-    }
+    pack_range<kWire, kU>(c, bucket, reinterpret_cast<uint4 *>(c.stage(c.rank, half)), lo, hi, n, scale);
     comm_barrier(c, 0, s);
 
     double part = 0.0;
-    for (size_t g = lo + threadIdx.x; g < hi; g += kCommThreads) {
-        uint4 w[DMLB_MAX_WORLD];
-#pragma unroll
-        for (int r = 0; r < DMLB_MAX_WORLD; ++r)
-            if (r < c.world) w[r] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.stage(r, half)) + g);
-        float acc[E];
-#pragma unroll
-        for (int j = 0; j < E; ++j) acc[j] = 0.0f;
-#pragma unroll
-        for (int r = 0; r < DMLB_MAX_WORLD; ++r)
-            if (r < c.world) W::accumulate(acc, w[r]);
-        part += store_bucket<E>(bucket, g, n, acc, sumsq_out != nullptr);
-    }
+    const bool want_sumsq = sumsq_out != nullptr;
+    reduce_range<kWire, kU>(c, half, lo, hi, 0, [&](size_t g, const float *acc) {
+        part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
+    });
     if (sumsq_out) {
         double tot = block_sum(part);
         if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
@@ -139,9 +186,10 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
 // two-shot: slice q (S wire vectors) is reduced by rank q.  CTA b owns vector range [b*per, (b+1)*per) of EVERY slice,
 // so it only ever depends on what the peers' CTA b wrote (per-CTA barriers suffice).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kWire>
+template <int kWire, int kU>
 __global__ void __launch_bounds__(kCommThreads, 2)
-allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S, float scale, double *sumsq_out) {
+allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S, float scale,
+                         double *sumsq_out) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
     const uint32_t s = comm_begin(c);
@@ -150,53 +198,44 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     const size_t lo = (size_t)blockIdx.x * per;
     const size_t hi = min(S, lo + per);
 
-    // phase 1 (K1): scale + cast my whole bucket into my staging half
+    // phase 1 (K1): scale + cast my whole bucket into my staging half, slice by slice
     uint4 *mine = reinterpret_cast<uint4 *>(c.stage(c.rank, half));
     for (int q = 0; q < c.world; ++q) {
-        for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
-            const size_t g = (size_t)q * S + i;
-            if (g < nvec) {
-                float v[E];
-                load_bucket<E>(bucket, g, n, scale, v);
-                mine[g] = W::pack(v);
-            }
-        }
+        const size_t off = (size_t)q * S;
+        if (off >= nvec) break;
+        pack_range<kWire, kU>(c, bucket, mine, off + lo, min(off + hi, nvec), n, scale);
     }
     comm_barrier(c, 0, s);
 
     // phase 2 (reduce-scatter): I reduce slice `rank` from every peer's staging into my result half
-    uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
-    for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
-        const size_t g = (size_t)c.rank * S + i;
-        if (g < nvec) {
-            uint4 w[DMLB_MAX_WORLD];
-#pragma unroll
-            for (int r = 0; r < DMLB_MAX_WORLD; ++r)
-                if (r < c.world) w[r] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.stage(r, half)) + g);
-            float acc[E];
-#pragma unroll
-            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
-#pragma unroll
-            for (int r = 0; r < DMLB_MAX_WORLD; ++r)
-                if (r < c.world) W::accumulate(acc, w[r]);
-            res[i] = W::pack(acc);
-        }
+    {
+        uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
+        const size_t off = (size_t)c.rank * S;
+        const size_t lim = off < nvec ? min(hi, nvec - off) : 0;
+        if (lo < lim)
+            reduce_range<kWire, kU>(c, half, lo, lim, off, [&](size_t i, const float *acc) { res[i] = W::pack(acc); });
     }
     comm_barrier(c, 1, s);
 
-    // phase 3 (all-gather + K2): pull every rank's reduced slice and widen into the fp32 bucket
+    // phase 3 (all-gather + K2): pull every rank's reduced slice (W loads in flight per thread) and widen into the bucket
     double part = 0.0;
-    for (int q = 0; q < c.world; ++q) {
-        const uint4 *rq = reinterpret_cast<const uint4 *>(c.result(q, half));
-        for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
+    const bool want_sumsq = sumsq_out != nullptr;
+    constexpr int kMaxW = DMLB_MAX_WORLD / kU;
+    for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
+        uint4 w[kMaxW];
+#pragma unroll
+        for (int q = 0; q < kMaxW; ++q)
+            if (q < c.world && (size_t)q * S + i < nvec)
+                w[q] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
+#pragma unroll
+        for (int q = 0; q < kMaxW; ++q) {
             const size_t g = (size_t)q * S + i;
-            if (g < nvec) {
-                uint4 w = ld_coherent_u4(rq + i);
+            if (q < c.world && g < nvec) {
                 float acc[E];
 #pragma unroll
                 for (int j = 0; j < E; ++j) acc[j] = 0.0f;
-                W::accumulate(acc, w);
-                part += store_bucket<E>(bucket, g, n, acc, sumsq_out != nullptr);
+                W::accumulate(acc, w[q]);
+                part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
             }
         }
     }
@@ -262,27 +301,31 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
     if (bytes > c->dev.msg_cap) return DMLB_ECAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
     const bool oneshot = algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || c->dev.world <= 2));
-    if (oneshot) {
-        size_t want = (nvec + kCommThreads - 1) / kCommThreads;
-        // big one-shot messages (W<=2 takes this path at any size): a few vectors per thread, at most 2 CTAs per SM
-        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
-        if (want > cap) want = cap;
-        int grid = (int)(want < 1 ? 1 : want);
-        if (wire == DMLB_WIRE_BF16)
-            allreduce_oneshot_kernel<DMLB_WIRE_BF16><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);
-        else
-            allreduce_oneshot_kernel<DMLB_WIRE_F32><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);
+    const int W = c->dev.world;
+    const int kU = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
+    const size_t items = oneshot ? nvec : (nvec + W - 1) / W;  // vectors a CTA grid is spread over
+    size_t want = (items + (size_t)kCommThreads * kU - 1) / ((size_t)kCommThreads * kU);
+    size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);  // all CTAs co-resident: the per-CTA barriers need that
+    if (want > cap) want = cap;
+    const int grid = (int)(want < 1 ? 1 : want);
+#define DMLB_LAUNCH_AR(WIRE, U)                                                                                       \
+    do {                                                                                                              \
+        if (oneshot)                                                                                                  \
+            allreduce_oneshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);  \
+        else                                                                                                          \
+            allreduce_twoshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items, scale,  \
+                                                                             sumsq);                                  \
+    } while (0)
+    if (wire == DMLB_WIRE_BF16) {
+        if (kU == 4) DMLB_LAUNCH_AR(DMLB_WIRE_BF16, 4);
+        else if (kU == 2) DMLB_LAUNCH_AR(DMLB_WIRE_BF16, 2);
+        else DMLB_LAUNCH_AR(DMLB_WIRE_BF16, 1);
     } else {
-        const size_t S = (nvec + c->dev.world - 1) / c->dev.world;
-        size_t want = (S + kCommThreads - 1) / kCommThreads;
-        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
-        if (want > cap) want = cap;
-        int grid = (int)(want < 1 ? 1 : want);
-        if (wire == DMLB_WIRE_BF16)
-            allreduce_twoshot_kernel<DMLB_WIRE_BF16><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, S, scale, sumsq);
-        else
-            allreduce_twoshot_kernel<DMLB_WIRE_F32><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, S, scale, sumsq);
+        if (kU == 4) DMLB_LAUNCH_AR(DMLB_WIRE_F32, 4);
+        else if (kU == 2) DMLB_LAUNCH_AR(DMLB_WIRE_F32, 2);
+        else DMLB_LAUNCH_AR(DMLB_WIRE_F32, 1);
     }
+#undef DMLB_LAUNCH_AR
     return launched();
 }
 
