@@ -350,6 +350,7 @@ def kernel_microbench(dev, peaks):
         return d
 
     pack = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
+    pack_tma = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16_tma(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
     unpack = timed(lambda: N.check(lib.dmlb_bucket_unpack_bf16_f32(wire.data_ptr(), src.data_ptr(), n, 1.0, None, st)))
     scale = timed(lambda: N.check(lib.dmlb_bucket_scale_f32(src.data_ptr(), n, 1.0, st)))
     sq = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -362,7 +363,8 @@ def kernel_microbench(dev, peaks):
                                 'the measured copy peak is a 50/50 read/write mix'},
         'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, n, pack,
                           'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2)'),
-        'roofline_more': [entry('dmlb_bucket_unpack_bf16_f32 (K2)', 6, n, unpack),
+        'roofline_more': [entry('dmlb_bucket_pack_f32_bf16_tma (K1, TMA bulk-load variant, A/B partner)', 6, n, pack_tma),
+                          entry('dmlb_bucket_unpack_bf16_f32 (K2)', 6, n, unpack),
                           entry('dmlb_bucket_scale_f32 (K1, fp32 wire, in place)', 8, n, scale)],
     }
     # ResNet-18 DDP buckets.  A single 10 us launch cannot be timed with an event pair (the pair itself

@@ -84,6 +84,9 @@ int dmlb_host_device_pointer(void *host, void **device);
 int dmlb_bucket_scale_f32(float *buf, size_t n, float scale, void *stream);
 int dmlb_bucket_pack_f32_f32(const float *src, float *dst, size_t n, float scale, void *stream);
 int dmlb_bucket_pack_f32_bf16(const float *src, uint16_t *dst, size_t n, float scale, void *stream);
+/* Same result as dmlb_bucket_pack_f32_bf16, loads issued as TMA bulk copies (cp.async.bulk -> shared memory, 4-stage
+ * mbarrier ring).  Kept as the measured A/B partner of the register path; needs 16-byte aligned pointers. */
+int dmlb_bucket_pack_f32_bf16_tma(const float *src, uint16_t *dst, size_t n, float scale, void *stream);
 /* dst = float(src) * scale.  If sumsq != NULL, also atomically adds sum(dst^2) (fp64) to *sumsq — the fused first
  * half of clip_grad_norm_ (reference stage.py:276-279), costing no extra HBM pass. */
 int dmlb_bucket_unpack_bf16_f32(const uint16_t *src, float *dst, size_t n, float scale, double *sumsq, void *stream);

@@ -79,6 +79,18 @@ class TestBucketKernels:
         assert (t.cpu().numpy() == want).all()
         np.testing.assert_allclose(sumsq.item(), np.sum(want.astype(np.float64) ** 2), rtol=1e-12)
 
+    @pytest.mark.parametrize('n', [0, 5, 4095, 4096, 4097, 3 * 4096, 600 * 4096 + 17, 11_689_512])
+    def test_tma_pack_variant_is_bit_identical(self, lib, n):
+        g = rand_grads(n, 5 + n)
+        src = torch.from_numpy(g).cuda()
+        a = torch.zeros(n + 8, dtype=torch.bfloat16, device='cuda')
+        b = torch.zeros(n + 8, dtype=torch.bfloat16, device='cuda')
+        N_().check(lib.dmlb_bucket_pack_f32_bf16(src.data_ptr(), a.data_ptr(), n, 0.125, sptr()))
+        N_().check(lib.dmlb_bucket_pack_f32_bf16_tma(src.data_ptr(), b.data_ptr(), n, 0.125, sptr()))
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        want = grad_oracle.f32_to_bf16_bits(grad_oracle.scale_f32(g, 8))
+        assert (b[:n].view(torch.int16).cpu().numpy().view(np.uint16) == want).all()
+
     @pytest.mark.parametrize('offset', [1, 2, 3])
     def test_misaligned_pointers_take_the_safe_path(self, lib, offset):
         n = 5000
