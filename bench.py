@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument('--grad-route', choices=['auto', 'peer', 'nccl'], default='auto')
     ap.add_argument('--metric-route', choices=['auto', 'peer', 'collective'], default='auto')
     ap.add_argument('--no-graph', action='store_true', help='eager step loop instead of the whole-step CUDA graph')
+    ap.add_argument('--channels-last', action='store_true', help='keep model + images in NHWC (cuDNN bf16 native layout)')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=3000)
@@ -61,48 +62,75 @@ def parse_args():
 # clocks
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The region can be as short as
+    0.1 s, so NVML is polled from a thread every 2 ms (an `nvidia-smi -lms` subprocess would not deliver a single sample
+    in that time); nvidia-smi is only the fallback when the NVML bindings are missing."""
+    REASONS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
-        self.path = Path(tempfile.mkdtemp(prefix='dmlb_clk_')) / 'clocks.csv'
-        self.proc = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100',
-                 '-i', str(self.gpu_index)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+            return
+        self._poll()  # at least one sample even for a very short region
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _poll(self):
+        nv = self._nvml
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle)) if hasattr(
+                nv, 'nvmlDeviceGetCurrentClocksEventReasons') else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+            for name, bit in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _run(self):
+        while not self._stop.wait(0.002):
+            self._poll()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
+        if self._nvml is None:
+            return self._smi_once()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        self._poll()
+        return {'sm_mhz': statistics.median(self.samples) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                'samples': len(self.samples), 'reasons': sorted(self.reasons), 'how': 'NVML polled every 2 ms'}
+
+    def _smi_once(self):
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.path.read_text().splitlines():
-            parts = [p.strip() for p in line.split(',')]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+            out = subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm,clocks.max.sm', '--format=csv,noheader,nounits',
+                                  '-i', str(self._physical_index())], capture_output=True, text=True, timeout=10).stdout
+            sm, mx = [float(v) for v in out.strip().split(',')[:2]]
+            return {'sm_mhz': sm, 'sm_max_mhz': mx, 'samples': 1, 'reasons': [], 'how': 'nvidia-smi, once, after the region'}
+        except Exception:  # noqa: BLE001
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'samples': 0, 'reasons': ['no NVML / nvidia-smi']}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -151,6 +179,8 @@ def native_arm(args):
             model = nn.Sequential(nn.Conv2d(1, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
                                   nn.Conv2d(16, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(),
                                   nn.Linear(784, 10))  # reference examples/mnist.py:27-36
+            if args.channels_last:
+                model = model.to(memory_format=torch.channels_last)
             self.pipeline.register_model('cnn', model, verbose=False, grad_wire=args.grad_wire)
             self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3,
                                                                       capturable=use_graph))
@@ -170,6 +200,8 @@ def native_arm(args):
         def step(self, batch):
             x, y = batch
             x = x.to(self.device, non_blocking=True)  # no-op for the resident phases
+            if args.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)  # C == 1: a stride relabel, no copy
             y = y.to(self.device, non_blocking=True)
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 out = self.pipeline.models['cnn'](x)
@@ -268,7 +300,7 @@ def native_arm(args):
         'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP, bf16 autocast, Adam, 32 samples/rank/step, '
                                '5 metrics tracked + cross-rank metric exchange every step',
                    'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'grad_wire': args.grad_wire,
-                   'cuda_graph': bool(stage._graph is not None),
+                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last),
                    'graph_replays': stage._graph.replays if stage._graph is not None else 0,
                    'grad_route': sorted(set(sync.last_routes.values())),
                    'metric_route': 'peer' if pipeline.metric_comm is not None else ('single' if world == 1 else 'collective'),
