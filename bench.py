@@ -383,6 +383,10 @@ def kernel_microbench(dev, peaks):
 
     pack = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
     pack_tma = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16_tma(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
+    pack_regs = timed(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16_regs(src.data_ptr(), wire.data_ptr(), n, 0.125, st)))
+    unpack_tma = timed(lambda: N.check(lib.dmlb_bucket_unpack_bf16_f32_tma(wire.data_ptr(), src.data_ptr(), n, 1.0, st)))
+    unpack_regs = timed(lambda: N.check(lib.dmlb_bucket_unpack_bf16_f32_regs(wire.data_ptr(), src.data_ptr(), n, 1.0,
+                                                                             None, st)))
     unpack = timed(lambda: N.check(lib.dmlb_bucket_unpack_bf16_f32(wire.data_ptr(), src.data_ptr(), n, 1.0, None, st)))
     scale = timed(lambda: N.check(lib.dmlb_bucket_scale_f32(src.data_ptr(), n, 1.0, st)))
     sq = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -393,10 +397,13 @@ def kernel_microbench(dev, peaks):
                         'write_only_GBps': round(n * 4 / statistics.mean(write_only) / 1e9, 1),
                         'note': 'read-only = dmlb_bucket_sumsq_f32 (4 B/el); write-only = torch zero_ fill (4 B/el); '
                                 'the measured copy peak is a 50/50 read/write mix'},
-        'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, n, pack,
+        'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1, default dispatch)', 6, n, pack,
                           'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2)'),
-        'roofline_more': [entry('dmlb_bucket_pack_f32_bf16_tma (K1, TMA bulk-load variant, A/B partner)', 6, n, pack_tma),
-                          entry('dmlb_bucket_unpack_bf16_f32 (K2)', 6, n, unpack),
+        'roofline_more': [entry('dmlb_bucket_pack_f32_bf16_tma (K1 via TMA bulk loads)', 6, n, pack_tma),
+                          entry('dmlb_bucket_pack_f32_bf16_regs (K1 via LDG.128 x4 in registers)', 6, n, pack_regs),
+                          entry('dmlb_bucket_unpack_bf16_f32 (K2, default dispatch)', 6, n, unpack),
+                          entry('dmlb_bucket_unpack_bf16_f32_tma (K2 via TMA bulk load + bulk store)', 6, n, unpack_tma),
+                          entry('dmlb_bucket_unpack_bf16_f32_regs (K2 via registers)', 6, n, unpack_regs),
                           entry('dmlb_bucket_scale_f32 (K1, fp32 wire, in place)', 8, n, scale)],
     }
     # ResNet-18 DDP buckets.  A single 10 us launch cannot be timed with an event pair (the pair itself
@@ -467,7 +474,7 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
     for i, name in enumerate(names):
         t.register_metric(name, ops[i % 4])
     vals = torch.randn(n_metrics, generator=torch.Generator().manual_seed(rank)).tolist()
-    live_us, live_host_us, epoch_us = [], [], []
+    live_us, live_host_us, epoch_us, pipe_us = [], [], [], []
     for it in range(warm + iters):
         for name, v in zip(names, vals):
             t.track(name, v)  # python floats ride as kernel immediates (31 per fold launch)
@@ -486,6 +493,17 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
             live_host_us.append((h1 - h0) * 1e6)
         if it % 10 == 9:
             assert live['m1'].value() is not None
+            # steady state: R exchanges back to back (ranks stay coupled through the kernels' own barrier, as in a
+            # step loop) -> per-call time without the launch skew a host barrier leaves behind
+            R = 10
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(R):
+                keep = t.reduce_live()
+            p1.record()
+            p1.synchronize()
+            if it >= warm:
+                pipe_us.append(p0.elapsed_time(p1) * 1e3 / R)
             a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a2.record()
             t.next_epoch()
@@ -498,7 +516,7 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
         xs = sorted(xs)
         return {'median': xs[len(xs) // 2], 'p99': xs[max(0, int(len(xs) * 0.99) - 1)], 'min': xs[0]}
 
-    mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us)}
+    mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us), 'pipe': stats(pipe_us)}
     box = [None] * world
     dist.all_gather_object(box, mine)
 
@@ -508,9 +526,12 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
     out = {'n_metrics': n_metrics, 'world': world, 'iters': iters, 'unit': 'us'}
     out.update(worst('live'))
     out['host_call'] = worst('host')
+    out['back_to_back'] = worst('pipe')
     out['next_epoch'] = worst('epoch')
     out['what'] = ('median/p99/min: CUDA-event time of MetricTracker.reduce_live() (fused reduce kernel + async D2H of the '
-                   'results) with all 1024 metrics holding a value; host_call: wall time of the Python call; next_epoch: '
+                   'results) with all 1024 metrics holding a value, issued right after a host barrier (includes the ranks\' launch skew); '
+                   'back_to_back: per call when 10 exchanges are issued back to back (steady state of a step loop); '
+                   'host_call: wall time of the Python call; next_epoch: '
                    'CUDA-event time of the epoch-closing reduce incl. its O(#metrics) host bookkeeping')
     return out
 

@@ -52,6 +52,9 @@ SIGNATURES = {
     'dmlb_bucket_pack_f32_f32': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
     'dmlb_bucket_pack_f32_bf16': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
     'dmlb_bucket_pack_f32_bf16_tma': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
+    'dmlb_bucket_pack_f32_bf16_regs': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
+    'dmlb_bucket_unpack_bf16_f32_tma': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
+    'dmlb_bucket_unpack_bf16_f32_regs': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p]),
     'dmlb_bucket_unpack_bf16_f32': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p]),
     'dmlb_bucket_round_bf16_f32': (c_int, [c_void_p, c_size_t, c_float, c_void_p, c_void_p]),
     'dmlb_bucket_sumsq_f32': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -168,6 +168,7 @@ class DeviceSlab:
         self.acc = self.cnt = self.desc = self.out = None
         self._host_pool = []
         self._event_pool = []
+        self._wr = None
         self._host_dptr = {}
         self._range_cache = {}
         self._host_mapped = None  # None = not probed yet; False = pinned memory is not device-mapped here (copy path)
@@ -188,6 +189,7 @@ class DeviceSlab:
         self.acc, self.cnt, self.desc = new['acc'], new['cnt'], new['desc']
         self.out = torch.zeros(STATUS_BYTES + 9 * capacity, dtype=torch.uint8, device=self.device)
         self.capacity = capacity
+        self._ptrs = (self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), self.out.data_ptr())
         self._host_pool = []
 
     def _lib(self):
@@ -276,6 +278,16 @@ class DeviceSlab:
                                              len(entries), N.stream_ptr()), 'metric_fold')
 
     # -- reduce ------------------------------------------------------------------------------------------------------
+    def _world_rank(self):
+        """(world, rank) of the exchange group; cached — a slab is bound to one process group for its lifetime."""
+        wr = self._wr
+        if wr is None or wr[2] is not self.group:
+            w, r = _world(self.group)
+            if not (dist.is_available() and dist.is_initialized()):
+                return w, r  # not cached: the group may be initialised later
+            wr = self._wr = (w, r, self.group)
+        return wr[0], wr[1]
+
     def _range_array(self, ranges):
         key = tuple(ranges)
         hit = self._range_cache.get(key)
@@ -293,12 +305,13 @@ class DeviceSlab:
         may differ between ranks).  Returns a _PendingResult (to_host) or None."""
         self.flush()
         lib = self._lib()
-        world, rank = _world(self.group)
+        world, rank = self._world_rank()
         if not exchange:
             world = 1
         st = N.stream_ptr()
         host = None
-        base = self.out.data_ptr()
+        acc_p, cnt_p, desc_p, out_p = self._ptrs
+        base = out_p
         if to_host:
             host, dptr = self._acquire_host()
             if dptr is not None:
@@ -310,9 +323,10 @@ class DeviceSlab:
             for arr, n in self._range_array(ranges):
                 if n == 0 and comm_handle is None:
                     continue
-                N.check(lib.dmlb_metric_reduce(comm_handle, self.acc.data_ptr(), self.cnt.data_ptr(),
-                                               self.desc.data_ptr(), self.n_cells, arr, n, layout_hash,
-                                               int(reset), val_ptr, flag_ptr, status_ptr, st), 'metric_reduce')
+                rc = lib.dmlb_metric_reduce(comm_handle, acc_p, cnt_p, desc_p, self.n_cells, arr, n, layout_hash,
+                                            int(reset), val_ptr, flag_ptr, status_ptr, st)
+                if rc:
+                    N.check(rc, 'metric_reduce')
 
         if world == 1:
             launch(None, list(global_ranges) + list(local_ranges))
@@ -326,7 +340,7 @@ class DeviceSlab:
                                         status_ptr, st)
         if not to_host:
             return None
-        if base == self.out.data_ptr():  # pinned memory not device-mapped on this platform: one D2H copy instead
+        if base == out_p:  # pinned memory not device-mapped on this platform: one D2H copy instead
             host.copy_(self.out, non_blocking=True)
         event = self._event()
         event.record()

@@ -84,9 +84,15 @@ int dmlb_host_device_pointer(void *host, void **device);
 int dmlb_bucket_scale_f32(float *buf, size_t n, float scale, void *stream);
 int dmlb_bucket_pack_f32_f32(const float *src, float *dst, size_t n, float scale, void *stream);
 int dmlb_bucket_pack_f32_bf16(const float *src, uint16_t *dst, size_t n, float scale, void *stream);
-/* Same result as dmlb_bucket_pack_f32_bf16, loads issued as TMA bulk copies (cp.async.bulk -> shared memory, 4-stage
- * mbarrier ring).  Kept as the measured A/B partner of the register path; needs 16-byte aligned pointers. */
+/* The two implementations behind dmlb_bucket_pack_f32_bf16 / dmlb_bucket_unpack_bf16_f32, exported so that the choice
+ * can be measured (bench.py roofline_more):
+ *   _tma  : TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a 4-stage mbarrier ring in shared memory — bulk loads for
+ *           K1, bulk loads AND bulk stores for K2.  Needs 16-byte aligned pointers; used for buckets >= 256 Ki elements.
+ *   _regs : 128-bit LDG/STG through registers, 4 loads in flight per thread.  Any alignment; used for small buckets. */
 int dmlb_bucket_pack_f32_bf16_tma(const float *src, uint16_t *dst, size_t n, float scale, void *stream);
+int dmlb_bucket_pack_f32_bf16_regs(const float *src, uint16_t *dst, size_t n, float scale, void *stream);
+int dmlb_bucket_unpack_bf16_f32_tma(const uint16_t *src, float *dst, size_t n, float scale, void *stream);
+int dmlb_bucket_unpack_bf16_f32_regs(const uint16_t *src, float *dst, size_t n, float scale, double *sumsq, void *stream);
 /* dst = float(src) * scale.  If sumsq != NULL, also atomically adds sum(dst^2) (fp64) to *sumsq — the fused first
  * half of clip_grad_norm_ (reference stage.py:276-279), costing no extra HBM pass. */
 int dmlb_bucket_unpack_bf16_f32(const uint16_t *src, float *dst, size_t n, float scale, double *sumsq, void *stream);

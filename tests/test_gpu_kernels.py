@@ -85,11 +85,19 @@ class TestBucketKernels:
         src = torch.from_numpy(g).cuda()
         a = torch.zeros(n + 8, dtype=torch.bfloat16, device='cuda')
         b = torch.zeros(n + 8, dtype=torch.bfloat16, device='cuda')
-        N_().check(lib.dmlb_bucket_pack_f32_bf16(src.data_ptr(), a.data_ptr(), n, 0.125, sptr()))
+        N_().check(lib.dmlb_bucket_pack_f32_bf16_regs(src.data_ptr(), a.data_ptr(), n, 0.125, sptr()))
         N_().check(lib.dmlb_bucket_pack_f32_bf16_tma(src.data_ptr(), b.data_ptr(), n, 0.125, sptr()))
         assert torch.equal(a.view(torch.int16), b.view(torch.int16))
         want = grad_oracle.f32_to_bf16_bits(grad_oracle.scale_f32(g, 8))
         assert (b[:n].view(torch.int16).cpu().numpy().view(np.uint16) == want).all()
+        # K2: TMA bulk load + bulk store vs the register path vs the oracle
+        x = torch.full((n + 4,), -3.0, device='cuda')
+        y = torch.full((n + 4,), -3.0, device='cuda')
+        N_().check(lib.dmlb_bucket_unpack_bf16_f32_regs(b.data_ptr(), x.data_ptr(), n, 2.0, None, sptr()))
+        N_().check(lib.dmlb_bucket_unpack_bf16_f32_tma(b.data_ptr(), y.data_ptr(), n, 2.0, sptr()))
+        assert torch.equal(x, y)
+        assert (y[:n].cpu().numpy() == grad_oracle.bf16_bits_to_f32(want) * np.float32(2.0)).all()
+        assert (y[n:].cpu().numpy() == -3.0).all()
 
     @pytest.mark.parametrize('offset', [1, 2, 3])
     def test_misaligned_pointers_take_the_safe_path(self, lib, offset):
