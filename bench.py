@@ -445,6 +445,13 @@ def kernel_microbench(dev, peaks):
         secs = [max(t - base, 1e-9) for t in graph_time(body)]
         buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, secs,
                              'cold: 256 MB L2 flush before each launch; graph-captured, flush time subtracted'))
+        for label, fn in (('regs', lib.dmlb_bucket_pack_f32_bf16_regs), ('tma', lib.dmlb_bucket_pack_f32_bf16_tma)):
+            def body_v(fn=fn):
+                flush.zero_()
+                N.check(fn(s.data_ptr(), w.data_ptr(), elems, 0.125, side_ptr()))
+
+            secs_v = [max(t - base, 1e-9) for t in graph_time(body_v)]
+            buckets.append(entry(f'dmlb_bucket_pack_f32_bf16_{label}', 6, elems, secs_v, f'cold, {label} path forced'))
         # the same bucket as the step sees it: just written by backward, i.e. L2-resident
         warm = graph_time(lambda: N.check(lib.dmlb_bucket_pack_f32_bf16(s.data_ptr(), w.data_ptr(), elems, 0.125,
                                                                          side_ptr())))

@@ -34,7 +34,9 @@ int sm_count() {
     return cached[dev];
 }
 
-constexpr size_t kTmaMinElems = 256 * 1024;  // below ~1 MB the mbarrier pipeline's fill/drain costs more than it saves
+// Measured A/B (profiles/README.md §2): the TMA ring wins by ~3.5 % on a 1 GiB bucket but its fill/drain costs ~2 us, so at
+// DDP's bucket sizes (<= 25 MiB; 44.6 MiB once) the register path is faster.  TMA takes over from 128 MiB of fp32 upward.
+constexpr size_t kTmaMinElems = 32u << 20;
 constexpr int kUnroll = 4;      // independent vector loads a thread issues before its first store
 constexpr int kCtasPerSm = 4;
 
@@ -301,7 +303,7 @@ int dmlb_bucket_pack_f32_bf16(const float *src, uint16_t *dst, size_t n, float s
     if ((!src || !dst) && n) return DMLB_EINVAL;
     if (((uintptr_t)src & 3) || ((uintptr_t)dst & 1)) return DMLB_EALIGN;
     if (n >= kTmaMinElems && (((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 15) == 0)
-        return dmlb_bucket_pack_f32_bf16_tma(src, dst, n, scale, stream);  // big + aligned: TMA bulk loads (0.98 vs 0.93)
+        return dmlb_bucket_pack_f32_bf16_tma(src, dst, n, scale, stream);  // huge + aligned: TMA bulk loads (0.96 vs 0.93)
     return pack_bf16_regs(src, dst, n, scale, stream);
 }
 

@@ -9,8 +9,9 @@
 //   empty[s]  : one arrive per consumer warp when the stage has been read                      (consumers -> producer)
 //
 // Whether this beats plain vectorised loads for a no-reuse streaming pass is an empirical question; bench.py's
-// `roofline_more` reports both and DESIGN.md §3 states the outcome (round 1: K1 0.98 vs 0.93 of the measured HBM peak).
-// dmlb_bucket_pack_f32_bf16 / dmlb_bucket_unpack_bf16_f32 dispatch to these for buckets >= 256 Ki elements.
+// `roofline_more` reports both and DESIGN.md §3 states the outcome (round 1, 1 GiB cold: K1 0.96 vs 0.93, K2 0.87 vs 0.85 of
+// the measured HBM peak; at 2-47 MB buckets the register path is faster by the ring's ~2 us fill/drain).
+// dmlb_bucket_pack_f32_bf16 / dmlb_bucket_unpack_bf16_f32 dispatch to these from 32 Mi elements upward.
 #include "dmlb_common.cuh"
 
 namespace dmlb {
@@ -175,6 +176,15 @@ unpack_bf16_tma_kernel(const uint16_t *__restrict__ src, float *__restrict__ dst
     }
 }
 
+// 3 CTAs (64 KB of ring each) per SM; the CTA count is chosen so that every CTA gets the same number of tiles (+-1):
+// "min(tiles, cap)" would leave e.g. 967 tiles on 444 CTAs as 2-or-3 tiles each, i.e. a third of the machine idle at the end.
+static int tma_grid(size_t n_tiles) {
+    const size_t cap = (size_t)sm_count() * 3;
+    if (n_tiles <= cap) return (int)n_tiles;
+    const size_t per_cta = (n_tiles + cap - 1) / cap;
+    return (int)((n_tiles + per_cta - 1) / per_cta);
+}
+
 }  // namespace dmlb
 
 using namespace dmlb;
@@ -194,8 +204,7 @@ int dmlb_bucket_pack_f32_bf16_tma(const float *src, uint16_t *dst, size_t n, flo
             DMLB_CUDA(cudaFuncSetAttribute(pack_bf16_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
-        size_t cap = (size_t)sm_count() * 3;
-        int grid = (int)(n_tiles < cap ? n_tiles : cap);
+        const int grid = tma_grid(n_tiles);
         pack_bf16_tma_kernel<<<grid, kTmaThreads, smem, st>>>(src, dst, n_tiles, scale);
         int rc = launched();
         if (rc != DMLB_OK) return rc;
@@ -219,8 +228,7 @@ int dmlb_bucket_unpack_bf16_f32_tma(const uint16_t *src, float *dst, size_t n, f
             DMLB_CUDA(cudaFuncSetAttribute(unpack_bf16_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
-        size_t cap = (size_t)sm_count() * 3;
-        int grid = (int)(n_tiles < cap ? n_tiles : cap);
+        const int grid = tma_grid(n_tiles);
         unpack_bf16_tma_kernel<<<grid, kTmaThreads, smem, st>>>(src, dst, n_tiles, scale);
         int rc = launched();
         if (rc != DMLB_OK) return rc;
