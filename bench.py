@@ -152,8 +152,9 @@ def native_arm(args):
     world, rank = dist.get_world_size(), dist.get_rank()
     if world != args.gpus:
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE is {world}: launch with torchrun --nproc-per-node {args.gpus}')
-    K, W = args.steps, max(3, args.warmup)
     use_graph = not args.no_graph
+    # graph mode spends 3 eager steps + 1 capture step before the first replay: keep all of that inside the warm-up
+    K, W = args.steps, max(8 if use_graph else 3, args.warmup)
     torch.backends.cudnn.benchmark = True
 
     def gen_batches(seed, count, pinned):
