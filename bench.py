@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument('--grad-route', choices=['auto', 'peer', 'nccl'], default='auto')
     ap.add_argument('--metric-route', choices=['auto', 'peer', 'collective'], default='auto')
     ap.add_argument('--no-graph', action='store_true', help='eager step loop instead of the whole-step CUDA graph')
+    ap.add_argument('--no-fused-adam', action='store_true', help='torch.optim.Adam(fused=False)')
     ap.add_argument('--channels-last', action='store_true', help='keep model + images in NHWC (cuDNN bf16 native layout)')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -184,9 +185,11 @@ def native_arm(args):
                 model = model.to(memory_format=torch.channels_last)
             self.pipeline.register_model('cnn', model, verbose=False, grad_wire=args.grad_wire)
             self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3,
-                                                                      capturable=use_graph))
+                                                                      capturable=use_graph,
+                                                                      fused=not args.no_fused_adam))
             self.loss = nn.CrossEntropyLoss()
-            self.cuda_graph = use_graph  # whole-step CUDA graph after 3 eager steps (graphstep.py)
+            # whole-step CUDA graph after 3 eager steps (graphstep.py); at W > 1 it needs the peer communicator
+            self.cuda_graph = use_graph and (world == 1 or self.pipeline.grad_syncs['cnn'].comm is not None)
             self.live_metrics_every = 1  # metrics cross ranks EVERY step (BASELINE configs 2/3)
             self.tracker.deferred = True
             host = gen_batches(100 + rank, W + K, pinned=True)
@@ -301,7 +304,7 @@ def native_arm(args):
         'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP, bf16 autocast, Adam, 32 samples/rank/step, '
                                '5 metrics tracked + cross-rank metric exchange every step',
                    'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'grad_wire': args.grad_wire,
-                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last),
+                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last), 'adam': 'torch fused' if not args.no_fused_adam else 'torch foreach',
                    'graph_replays': stage._graph.replays if stage._graph is not None else 0,
                    'grad_route': sorted(set(sync.last_routes.values())),
                    'metric_route': 'peer' if pipeline.metric_comm is not None else ('single' if world == 1 else 'collective'),

@@ -69,6 +69,7 @@ SIGNATURES = {
     'dmlb_comm_destroy': (c_int, [c_void_p]),
     'dmlb_comm_allreduce': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p, c_int, c_void_p]),
     'dmlb_comm_barrier': (c_int, [c_void_p, c_void_p]),
+    'dmlb_comm_error': (c_int, [c_void_p, POINTER(c_int)]),
     'dmlb_metric_reset': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'dmlb_metric_fold': (c_int, [c_void_p, c_void_p, c_void_p, POINTER(FoldEntry), c_int, c_void_p]),
     'dmlb_metric_reduce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(Range), c_int, c_uint64,

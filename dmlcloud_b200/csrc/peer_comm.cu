@@ -329,6 +329,16 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
     return launched();
 }
 
+int dmlb_comm_error(void *comm, int *error) {
+    if (!comm || !error) return DMLB_EINVAL;
+    Comm *c = reinterpret_cast<Comm *>(comm);
+    uint32_t word = 0;
+    // the error word lives in this rank's own arena (control block, word 2); a blocking 4-byte read: call it per epoch
+    DMLB_CUDA(cudaMemcpy(&word, c->dev.arena[c->dev.rank] + 2 * sizeof(uint32_t), sizeof(word), cudaMemcpyDeviceToHost));
+    *error = (int)word;
+    return DMLB_OK;
+}
+
 int dmlb_comm_barrier(void *comm, void *stream) {
     if (!comm) return DMLB_EINVAL;
     Comm *c = reinterpret_cast<Comm *>(comm);

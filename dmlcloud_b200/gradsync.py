@@ -89,6 +89,16 @@ class PeerComm:
     def fits(self, wire_bytes):
         return wire_bytes <= self.max_message_bytes
 
+    def check(self):
+        """Raise if a collective on this communicator timed out waiting for a peer (blocking: call per epoch)."""
+        if self.handle is None:
+            return
+        err = ctypes.c_int(0)
+        N.check(N.cuda_lib(self.device.index).dmlb_comm_error(self.handle, ctypes.byref(err)), 'comm_error')
+        if err.value:
+            raise RuntimeError('a peer did not arrive at a libdmlb barrier within 10 s: a rank died or the ranks issued '
+                               'different collectives; gradients / metrics of that step are invalid')
+
     def barrier(self, stream=None):
         N.check(N.cuda_lib(self.device.index).dmlb_comm_barrier(self.handle, N.stream_ptr(stream)), 'comm_barrier')
 

@@ -298,6 +298,9 @@ class TrainingPipeline:
         pass
 
     def _post_epoch(self):
+        for comm in [self.metric_comm] + [s.comm for s in self.grad_syncs.values()]:
+            if comm is not None:
+                comm.check()  # a timed-out peer barrier surfaces here, once per epoch
         if self.wandb and is_root():
             import wandb
 

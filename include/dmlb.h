@@ -140,8 +140,11 @@ int dmlb_comm_destroy(void *comm);
  * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot. */
 int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float scale, double *sumsq, int algo,
                         void *stream);
-/* all-gather of small fixed-size records through the arena (metric slab exchange building block; used by tests) */
+/* one flag barrier across all ranks on `stream` (setup / tests) */
 int dmlb_comm_barrier(void *comm, void *stream);
+/* *error != 0 after a peer failed to arrive at a barrier within 10 s (the kernels then fall through instead of hanging
+ * the GPU; results of that collective are garbage).  Blocking 4-byte device read: poll it per epoch, not per step. */
+int dmlb_comm_error(void *comm, int *error);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K3 / K4 — device-resident metric slab                                                                              */
