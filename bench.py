@@ -346,6 +346,26 @@ def load_peaks():
     return {'hbm_gbs': 6650.0, 'source': 'B200_PROFILING.md fallback (of fallback)'}
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes (read + write) per launch of a kernel from the committed `ncu --set full` summary of the same 1 GiB
+    launch (profiles/r1_bucket_kernels_ncu_full_final.csv, made by profiles/summarize_ncu.py); None if absent."""
+    import csv
+
+    path = ROOT / 'profiles' / 'r1_bucket_kernels_ncu_full_final.csv'
+    if not path.exists():
+        return None
+    rows = list(csv.reader(open(path)))
+    head = rows[0]
+    try:
+        k, t = head.index('Kernel Name'), head.index('dram_bytes_total')
+    except ValueError:
+        return None
+    for r in rows[2:]:
+        if kernel_substr in r[k]:
+            return int(float(r[t]))
+    return None
+
+
 def kernel_microbench(dev, peaks):
     """The bucket kernels through the C ABI on buffers far larger than L2 (1 GiB fp32 source), CUDA-event timed per launch
     on the launching stream; plus the ResNet-18 bucket sizes with an L2 flush between launches."""
@@ -396,13 +416,18 @@ def kernel_microbench(dev, peaks):
     sq = torch.zeros(1, dtype=torch.float64, device=dev)
     read_only = timed(lambda: N.check(lib.dmlb_bucket_sumsq_f32(src.data_ptr(), n, sq.data_ptr(), st)))
     write_only = timed(lambda: src.zero_())  # cudaMemset-class fill by torch: context for the write-heavy kernels
+    traffic = {'pack': ncu_traffic('pack_bf16_tma_kernel'), 'pack_regs': ncu_traffic('PackBf16'),
+               'unpack_tma': ncu_traffic('unpack_bf16_tma_kernel'), 'unpack_regs': ncu_traffic('UnpackBf16'),
+               'scale': ncu_traffic('ScaleInplace')}
     out = {
         'hbm_context': {'read_only_GBps': round(n * 4 / statistics.mean(read_only) / 1e9, 1),
                         'write_only_GBps': round(n * 4 / statistics.mean(write_only) / 1e9, 1),
                         'note': 'read-only = dmlb_bucket_sumsq_f32 (4 B/el); write-only = torch zero_ fill (4 B/el); '
                                 'the measured copy peak is a 50/50 read/write mix'},
         'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1, default dispatch)', 6, n, pack,
-                          'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2)'),
+                          'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2); '
+                          'traffic = dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed '
+                          'ncu --set full capture (profiles/r1_bucket_kernels_ncu_full_final.csv)'),
         'roofline_more': [entry('dmlb_bucket_pack_f32_bf16_tma (K1 via TMA bulk loads)', 6, n, pack_tma),
                           entry('dmlb_bucket_pack_f32_bf16_regs (K1 via LDG.128 x4 in registers)', 6, n, pack_regs),
                           entry('dmlb_bucket_unpack_bf16_f32 (K2, default dispatch)', 6, n, unpack),
@@ -462,6 +487,12 @@ def kernel_microbench(dev, peaks):
         buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, warm,
                              'warm: source L2-resident (as right after backward); back-to-back in a graph'))
     out['roofline_resnet18_buckets'] = buckets
+    out['roofline']['traffic'] = traffic['pack']
+    for e in out['roofline_more']:
+        for key, sub in (('pack_regs', '_regs (K1'), ('pack', '_tma (K1'), ('unpack_tma', 'f32_tma'), ('unpack_regs', 'f32_regs'),
+                         ('scale', 'scale_f32')):
+            if sub in e['kernel']:
+                e['traffic'] = traffic[key]
     del src, wire, flush
     torch.cuda.empty_cache()
     return out

@@ -937,6 +937,8 @@ class MetricTracker:
     def load_state_dict(self, state):
         self.epoch = state['epoch']
         self._histories = {name: list(history) for name, history in state['histories'].items()}
+        self._version += 1
+        self._live_plan = None
         self.reducers = {}
         for name, reducer_state in state['reducers'].items():
             metric = SlabMetric(self, name)

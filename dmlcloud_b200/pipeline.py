@@ -72,6 +72,7 @@ class TrainingPipeline:
         self.grad_syncs = {}               # model name -> gradsync.GradBucketSync
         self.metric_comm = None
         self.compute_stream = None         # dedicated stream all stage work runs on (created in run())
+        self._pending_state = {'models': {}, 'optimizers': {}, 'schedulers': {}}  # resumed state awaiting registration
         self._save_policy = {}
 
     @property
@@ -100,6 +101,8 @@ class TrainingPipeline:
             model.register_comm_hook(sync, sync.hook)
             self.grad_syncs[name] = sync
         self.models[name] = model
+        if name in self._pending_state['models']:  # resumed run: the snapshot was loaded before the stage built its model
+            _bare(model).load_state_dict(self._pending_state['models'].pop(name))
         self._save_policy[name] = dict(latest=save_latest, interval=save_interval, best=save_best,
                                        metric=best_metric, best_value=None)
         if verbose:
@@ -112,8 +115,12 @@ class TrainingPipeline:
 
     def register_optimizer(self, name: str, optimizer, scheduler=None):
         _claim(self.optimizers, 'Optimizer', name, optimizer)
+        if name in self._pending_state['optimizers']:
+            optimizer.load_state_dict(self._pending_state['optimizers'].pop(name))
         if scheduler is not None:
             self.schedulers[name] = scheduler
+            if name in self._pending_state['schedulers']:
+                scheduler.load_state_dict(self._pending_state['schedulers'].pop(name))
 
     def register_dataset(self, name: str, dataset: Union[Sequence, Any], verbose: bool = True):
         _claim(self.datasets, 'Dataset', name, dataset)
@@ -321,20 +328,33 @@ class TrainingPipeline:
         }
 
     def load_state_dict(self, state, strict=True):
+        """Restore a snapshot made by state_dict().  Models / optimizers / schedulers that are not registered yet (stages
+        usually build them in pre_stage, after resume_run) are kept and applied by the register_* call that brings them."""
         for k, sd in state.get('models', {}).items():
             if k in self.models:
                 _bare(self.models[k]).load_state_dict(sd, strict=strict)
+            else:
+                self._pending_state['models'][k] = sd
         for kind in ('optimizers', 'schedulers'):
             mine = getattr(self, kind)
             for k, sd in state.get(kind, {}).items():
                 if k in mine:
                     mine[k].load_state_dict(sd)
+                else:
+                    self._pending_state[kind][k] = sd
         if 'tracker' in state:
             self.tracker.load_state_dict(state['tracker'])
-            self.tracker.bind(device=self.device, comm=self.metric_comm, group=None)
         idx, epoch = state.get('stage_index'), state.get('stage_epoch')
         if idx is not None and epoch is not None and idx < len(self.stages):
             self.stages[idx].current_epoch = epoch
+
+    def load_checkpoint(self, tag: str = 'latest', strict=True):
+        """resume_run() helper: load `state/<tag>.pt` from the checkpoint directory (every rank reads the same file).
+        Returns False when the directory holds no such snapshot."""
+        if not self.checkpointing_enabled or not self.checkpoint_dir.has_state(tag):
+            return False
+        self.load_state_dict(self.checkpoint_dir.load_state(tag), strict=strict)
+        return True
 
     def _save_epoch_state(self):
         """End of epoch, metrics already reduced.  All ranks assemble the state (the tracker export is a plain D2H

@@ -373,6 +373,65 @@ class TestPipelineHost:
         assert '[Train] Loss' in (ck.log_file.read_text() + capsys.readouterr().out)
 
 
+    def test_resume_restores_epochs_bit_exactly(self, tmp_path):
+        """BASELINE config 3: checkpoint every epoch, resume -> tracker.epoch / stage.current_epoch / histories continue
+        exactly where they stopped (the reference only creates the directory)."""
+        from dmlcloud_b200 import TrainValStage
+        from dmlcloud_b200.pipeline import TrainingPipeline
+
+        class CpuPipeline(TrainingPipeline):
+            def _select_device(self):
+                return torch.device('cpu')
+
+            def _bind_metric_path(self):
+                self.tracker.bind(slab=OracleSlab())
+
+            def resume_run(self):
+                assert self.load_checkpoint('latest')
+
+        class S(TrainValStage):
+            def pre_stage(self):
+                torch.manual_seed(0)
+                self.model = torch.nn.Linear(4, 3)
+                self.pipeline.register_model('m', self.model, use_ddp=False, verbose=False)
+                self.pipeline.register_optimizer('sgd', torch.optim.SGD(self.model.parameters(), lr=0.1, momentum=0.9))
+                g = torch.Generator().manual_seed(1)
+                data = [(torch.randn(8, 4, generator=g), torch.randint(0, 3, (8,), generator=g)) for _ in range(4)]
+                self.pipeline.register_dataset('train', data, verbose=False)
+                self.pipeline.register_dataset('val', data[:1], verbose=False)
+
+            def step(self, batch):
+                x, y = batch
+                return torch.nn.functional.cross_entropy(self.model(x), y)
+
+        def run(root, epochs, resume):
+            _dummy_group()
+            try:
+                p = CpuPipeline(name='resume')
+                p.enable_checkpointing(str(root), resume=resume)
+                s = S()
+                p.append_stage(s, max_epochs=epochs)
+                p.run()
+                return p, s
+            finally:
+                from dmlcloud_b200.util.distributed import deinitialize_torch_distributed
+
+                deinitialize_torch_distributed()
+
+        full, _ = run(tmp_path / 'full', 4, False)                       # 4 epochs in one go
+        first, s1 = run(tmp_path / 'split', 2, False)                    # 2 epochs ...
+        assert s1.current_epoch == 3 and first.tracker.epoch == 3
+        resumed, s2 = run(first.checkpoint_dir.path, 4, True)            # ... then resume the same directory
+        assert resumed.resumed and s2.current_epoch == 5 and resumed.tracker.epoch == 5
+        for name in ('train/loss', 'val/loss', 'misc/total_train_batches', 'misc/epoch'):
+            a, b = full.tracker[name], resumed.tracker[name]
+            assert len(a) == len(b) == 4
+            for x, y in zip(a, b):
+                assert (x == y) if not isinstance(x, torch.Tensor) else torch.equal(x, y), name  # bit-exact continuation
+        for pa, pb in zip(full.models['m'].parameters(), resumed.models['m'].parameters()):
+            assert torch.equal(pa, pb)
+
+
 # ------------------------------------------------------------------------------------------------------ W = 2 over gloo
 def _w2_metrics_worker(rank, world, initfile, outdir):
     init_gloo(rank, world, initfile)
