@@ -248,3 +248,72 @@ def test_ddp_multi_bucket_overlap_w2(route, wire):
         assert res['buckets'] >= 3 and res['routes'] == [route], res
         # fp32: cuBLAS run-to-run reproducibility of the two backward passes only; bf16: one bf16 ulp on the sum
         assert res['worst'] <= (1e-5 if wire == 'fp32' else 4e-3), res
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4: ResNet-18 under DDP — the real bucket layout (44.6 MiB first, then 513,000 / 7,213,056 / 3,963,456
+# elements after DDP rebuilds its buckets), through the hook, two-shot sized messages included.
+# ----------------------------------------------------------------------------------------------------------------------
+def _resnet_worker(rank, world, initfile, outdir, wire):
+    init_gloo(rank, world, initfile)
+    import copy
+
+    import torch.distributed as dist
+    import torchvision
+    from torch.nn.parallel import DistributedDataParallel
+
+    from dmlcloud_b200.gradsync import GradBucketSync
+    from helpers import rank_device
+
+    di = rank_device(rank)
+    torch.cuda.set_device(di)
+    dev = torch.device('cuda', di)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18().to(dev)
+    shadow = copy.deepcopy(model)
+    ddp = DistributedDataParallel(model, broadcast_buffers=False, device_ids=[dev])
+    sync = GradBucketSync(dev, wire=wire, route='peer', max_message_bytes=64 << 20)
+    sizes = []
+    inner = sync.hook
+
+    def recording_hook(state, bucket):
+        sizes.append(bucket.buffer().numel())
+        return inner(state, bucket)
+
+    ddp.register_comm_hook(sync, recording_hook)
+    g = torch.Generator().manual_seed(7 + rank)
+    worst, per_step_sizes = 0.0, []
+    for step in range(3):
+        sizes.clear()
+        x = torch.randn(4, 3, 64, 64, generator=g).to(dev)
+        y = torch.randint(0, 1000, (4,), generator=g).to(dev)
+        for m in (ddp, shadow):
+            m.zero_grad()
+            torch.nn.functional.cross_entropy(m(x), y).backward()
+        local = torch.cat([p.grad.flatten() for p in shadow.parameters()])
+        both = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(both, local)  # gloo moves the CUDA tensors for the check
+        want = torch.stack(both).double().mean(0)
+        got = torch.cat([p.grad.flatten() for p in model.parameters()]).double()
+        worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+        per_step_sizes.append(sorted(sizes))
+    Path(outdir, f'r{rank}.json').write_text(json.dumps({'worst': worst, 'sizes': per_step_sizes,
+                                                         'routes': sorted(set(sync.last_routes.values()))}))
+    dist.barrier()
+    sync.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('wire', ['fp32', 'bf16'])
+def test_resnet18_ddp_buckets_through_the_hook_w2(wire):
+    pytest.importorskip('torchvision')
+    out = spawn(_resnet_worker, 2, wire, timeout=900)
+    for r in range(2):
+        res = json.loads((out / f'r{r}.json').read_text())
+        assert res['routes'] == ['peer'], res
+        assert res['sizes'][0] == [11_689_512]  # iteration 0: one 44.6 MiB bucket
+        assert res['sizes'][-1] == sorted([513_000, 7_213_056, 3_963_456])  # after DDP's bucket rebuild
+        # vs the fp64 mean of the per-rank gradients of an independent backward pass (cuDNN run-to-run noise included)
+        assert res['worst'] <= (2e-5 if wire == 'fp32' else 1e-2), res
