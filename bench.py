@@ -516,7 +516,7 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
     for i, name in enumerate(names):
         t.register_metric(name, ops[i % 4])
     vals = torch.randn(n_metrics, generator=torch.Generator().manual_seed(rank)).tolist()
-    live_us, live_host_us, epoch_us, pipe_us = [], [], [], []
+    live_us, live_host_us, epoch_us, pipe_us, dev_us = [], [], [], [], []
     for it in range(warm + iters):
         for name, v in zip(names, vals):
             t.track(name, v)  # python floats ride as kernel immediates (31 per fold launch)
@@ -546,6 +546,17 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
             p1.synchronize()
             if it >= warm:
                 pipe_us.append(p0.elapsed_time(p1) * 1e3 / R)
+            # pure device latency: a peer-barrier kernel first lines the GPUs up in time (every rank has already queued
+            # its exchange behind it), so the event pair sees no host launch skew
+            if pipeline.metric_comm is not None:
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                pipeline.metric_comm.barrier()
+                d0.record()
+                keep = t.reduce_live()
+                d1.record()
+                d1.synchronize()
+                if it >= warm:
+                    dev_us.append(d0.elapsed_time(d1) * 1e3)
             a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a2.record()
             t.next_epoch()
@@ -558,7 +569,8 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
         xs = sorted(xs)
         return {'median': xs[len(xs) // 2], 'p99': xs[max(0, int(len(xs) * 0.99) - 1)], 'min': xs[0]}
 
-    mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us), 'pipe': stats(pipe_us)}
+    mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us), 'pipe': stats(pipe_us),
+            'dev': stats(dev_us) if dev_us else stats(pipe_us)}
     box = [None] * world
     dist.all_gather_object(box, mine)
 
@@ -569,10 +581,12 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=2
     out.update(worst('live'))
     out['host_call'] = worst('host')
     out['back_to_back'] = worst('pipe')
+    out['device_aligned'] = worst('dev')
     out['next_epoch'] = worst('epoch')
     out['what'] = ('median/p99/min: CUDA-event time of MetricTracker.reduce_live() (fused reduce kernel + async D2H of the '
                    'results) with all 1024 metrics holding a value, issued right after a host barrier (includes the ranks\' launch skew); '
                    'back_to_back: per call when 10 exchanges are issued back to back (steady state of a step loop); '
+                   'device_aligned (W>1): one exchange queued behind a peer-barrier kernel, i.e. without host launch skew; '
                    'host_call: wall time of the Python call; next_epoch: '
                    'CUDA-event time of the epoch-closing reduce incl. its O(#metrics) host bookkeeping')
     return out
