@@ -98,21 +98,21 @@ __device__ __forceinline__ double store_bucket(float *bucket, size_t g, size_t n
 // kU vectors x W ranks into registers before the first add (kU = 4 for W <= 2, 2 for W <= 4, 1 for W <= 8 keeps the
 // register budget at ~32 data registers).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kWire, int kU>
+template <int kWire, int kU, int kStride = kCommThreads>
 __device__ __forceinline__ double pack_range(const CommDev &c, const float *bucket, uint4 *mine, size_t lo, size_t hi,
-                                             size_t n, float scale) {
+                                             size_t n, float scale, int tid = threadIdx.x) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
-    for (size_t g0 = lo + threadIdx.x; g0 < hi; g0 += (size_t)kCommThreads * kU) {
+    for (size_t g0 = lo + tid; g0 < hi; g0 += (size_t)kStride * kU) {
         float v[kU][E];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t g = g0 + (size_t)u * kCommThreads;
+            const size_t g = g0 + (size_t)u * kStride;
             if (g < hi) load_bucket<E>(bucket, g, n, scale, v[u]);
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t g = g0 + (size_t)u * kCommThreads;
+            const size_t g = g0 + (size_t)u * kStride;
             if (g < hi) mine[g] = W::pack(v[u]);
         }
     }
@@ -120,16 +120,17 @@ __device__ __forceinline__ double pack_range(const CommDev &c, const float *buck
 }
 
 // out(g) = sum over ranks of stage[r][g] for g in [lo, hi) (index space of the staging buffers, offset `goff`)
-template <int kWire, int kU, class Sink>
-__device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t lo, size_t hi, size_t goff, Sink sink) {
+template <int kWire, int kU, int kStride = kCommThreads, class Sink>
+__device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t lo, size_t hi, size_t goff, Sink sink,
+                                             int tid = threadIdx.x) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
     constexpr int kMaxW = DMLB_MAX_WORLD / kU;  // the host picks kU so that world <= kMaxW: kU x kMaxW = 8 vectors in flight
-    for (size_t i0 = lo + threadIdx.x; i0 < hi; i0 += (size_t)kCommThreads * kU) {
+    for (size_t i0 = lo + tid; i0 < hi; i0 += (size_t)kStride * kU) {
         uint4 w[kU][kMaxW];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t i = i0 + (size_t)u * kCommThreads;
+            const size_t i = i0 + (size_t)u * kStride;
             if (i < hi) {
 #pragma unroll
                 for (int r = 0; r < kMaxW; ++r)
@@ -138,7 +139,7 @@ __device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t 
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t i = i0 + (size_t)u * kCommThreads;
+            const size_t i = i0 + (size_t)u * kStride;
             if (i < hi) {
                 float acc[E];
 #pragma unroll
@@ -178,6 +179,77 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     if (sumsq_out) {
         double tot = block_sum(part);
         if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
+    }
+    comm_end(c, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// one-shot, tile-pipelined: the CTA's range is cut into chunks; warps 0-3 only pack (HBM: read fp32, write wire dtype),
+// warps 4-7 only reduce (NVLink: read every rank's staging chunk, sum, write fp32).  Chunk k+1 is being packed while the
+// peers' chunk k crosses NVLink, so the HBM pass and the NVLink pass overlap INSIDE the kernel instead of running as two
+// phases.  Per-chunk flags live in flag region 2 with values (s << 8) | (k + 1): monotonic across collectives, so the
+// ">= target" test of the non-pipelined kernels carries over; the staging double buffer gives the same WAR guarantee.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRole = 128;  // threads per role
+__device__ __forceinline__ void role_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kRole) : "memory"); }
+
+template <int kWire, int kU>
+__global__ void __launch_bounds__(2 * kRole, 2)
+allreduce_oneshot_pipelined_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec,
+                                   size_t chunk, float scale, double *sumsq_out) {
+    typedef Wire<kWire> W;
+    constexpr int E = W::kElems;
+    const uint32_t s = comm_begin(c);
+    const int half = s & 1;
+    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = min(nvec, lo + per);
+    const int n_chunks = hi > lo ? (int)((hi - lo + chunk - 1) / chunk) : 0;
+    const uint32_t base = s << 8;
+    const bool reducer = threadIdx.x >= kRole;
+    const int tid = threadIdx.x & (kRole - 1);
+
+    if (!reducer) {
+        uint4 *mine = reinterpret_cast<uint4 *>(c.stage(c.rank, half));
+        for (int k = 0; k < n_chunks; ++k) {
+            const size_t clo = lo + (size_t)k * chunk, chi = min(hi, clo + chunk);
+            pack_range<kWire, kU, kRole>(c, bucket, mine, clo, chi, n, scale, tid);
+            __threadfence_system();
+            role_sync(1);
+            if (tid < c.world) st_release_sys(c.flags(tid, 2, blockIdx.x) + c.rank, base + (uint32_t)k + 1u);
+        }
+    } else {
+        double part = 0.0;
+        const bool want_sumsq = sumsq_out != nullptr;
+        for (int k = 0; k < n_chunks; ++k) {
+            const size_t clo = lo + (size_t)k * chunk, chi = min(hi, clo + chunk);
+            if (tid < c.world) {
+                const uint32_t *mine = c.flags(c.rank, 2, blockIdx.x) + tid;
+                const uint32_t target = base + (uint32_t)k + 1u;
+                const unsigned long long t0 = globaltimer_ns();
+                while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {
+                    if (globaltimer_ns() - t0 > c.timeout_ns) {
+                        atomicExch(c.err(), 1u);
+                        break;
+                    }
+                }
+            }
+            role_sync(2);
+            reduce_range<kWire, kU, kRole>(c, half, clo, chi, 0, [&](size_t g, const float *acc) {
+                part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
+            }, tid);
+        }
+        if (want_sumsq) {  // reduce over the 4 reducer warps only
+            __shared__ double s_red[kRole / 32];
+            part = warp_sum(part);
+            if ((tid & 31) == 0) s_red[tid >> 5] = part;
+            role_sync(2);
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < kRole / 32; ++w) tot += s_red[w];
+                if (tot != 0.0) atomicAdd(sumsq_out, tot);
+            }
+        }
     }
     comm_end(c, s);
 }
@@ -253,6 +325,8 @@ __global__ void __launch_bounds__(kCommThreads) barrier_kernel(const __grid_cons
 }
 
 constexpr size_t kOneshotMaxBytes = 512 * 1024;
+constexpr size_t kPipelineMinBytes = 1 << 20;  // below ~1 MB a single pack/barrier/reduce round is already latency-bound
+constexpr bool kPipelineDefault = false;       // flipped once the N=2 sweep shows it ahead (profiles/)
 
 }  // namespace dmlb
 
@@ -300,6 +374,30 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
     const size_t bytes = nvec * 16;
     if (bytes > c->dev.msg_cap) return DMLB_ECAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool pipelined = algo == 3 || (algo == 0 && kPipelineDefault && c->dev.world <= 2 && bytes >= kPipelineMinBytes);
+    if (pipelined) {
+        const int W = c->dev.world;
+        const size_t chunk = 1024;  // wire vectors per chunk per CTA (16 KB)
+        size_t want = (nvec + 4 * chunk - 1) / (4 * chunk);  // ~4 chunks per CTA before spreading wider
+        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
+        if (want > cap) want = cap;
+        const int grid = (int)(want < 1 ? 1 : want);
+        const size_t per = (nvec + grid - 1) / grid;
+        if ((per + chunk - 1) / chunk > 250) return DMLB_ECAPACITY;  // chunk index must fit the flag's low 8 bits
+#define DMLB_LAUNCH_PIPE(WIRE, U) \
+    allreduce_oneshot_pipelined_kernel<WIRE, U><<<grid, 2 * kRole, 0, st>>>(c->dev, bucket, n, nvec, chunk, scale, sumsq)
+        if (wire == DMLB_WIRE_BF16) {
+            if (W <= 2) DMLB_LAUNCH_PIPE(DMLB_WIRE_BF16, 4);
+            else if (W <= 4) DMLB_LAUNCH_PIPE(DMLB_WIRE_BF16, 2);
+            else DMLB_LAUNCH_PIPE(DMLB_WIRE_BF16, 1);
+        } else {
+            if (W <= 2) DMLB_LAUNCH_PIPE(DMLB_WIRE_F32, 4);
+            else if (W <= 4) DMLB_LAUNCH_PIPE(DMLB_WIRE_F32, 2);
+            else DMLB_LAUNCH_PIPE(DMLB_WIRE_F32, 1);
+        }
+#undef DMLB_LAUNCH_PIPE
+        return launched();
+    }
     const bool oneshot = algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || c->dev.world <= 2));
     const int W = c->dev.world;
     const int kU = W <= 2 ? 4 : (W <= 4 ? 2 : 1);

@@ -137,7 +137,8 @@ size_t dmlb_comm_arena_bytes(size_t max_message_bytes);
 int dmlb_comm_create(void **comm, int world, int rank, void *const *arenas, size_t max_message_bytes);
 int dmlb_comm_destroy(void *comm);
 /* in-place averaged all-reduce of an fp32 bucket: bucket = sum_r wire(bucket_r * scale)  (scale = 1/W).
- * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot. */
+ * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot, 3 one-shot tile-pipelined (pack warps
+ * and reduce warps of a CTA work on different chunks at the same time; per-chunk flags). */
 int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float scale, double *sumsq, int algo,
                         void *stream);
 /* one flag barrier across all ranks on `stream` (setup / tests) */

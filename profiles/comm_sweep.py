@@ -76,6 +76,29 @@ def main():
                     b.synchronize()
                     times.append(a.elapsed_time(b) * 1e3 / R)
             fused_us = gather_max(statistics.median(times[1:]))
+            # ---- tile-pipelined one-shot (algo 3), same timing method ----
+            pipe_us = None
+            if wire_bytes >= (1 << 20):
+                with torch.cuda.stream(side):
+                    g3 = torch.cuda.CUDAGraph()
+                    N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, 3,
+                                                    N.stream_ptr(side)))
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    with torch.cuda.graph(g3, stream=side):
+                        for _ in range(R):
+                            N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, 3,
+                                                            N.stream_ptr(side)))
+                    t3 = []
+                    for _ in range(6):
+                        dist.barrier()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        g3.replay()
+                        b.record()
+                        b.synchronize()
+                        t3.append(a.elapsed_time(b) * 1e3 / R)
+                pipe_us = gather_max(statistics.median(t3[1:]))
             # ---- NCCL route ----
             buf2 = base.clone()
             stage = torch.empty(n, dtype=torch.bfloat16, device=dev) if wire == 'bf16' else None
@@ -112,7 +135,8 @@ def main():
                 return {'us': round(us, 2), 'bus_GBps': round(gbps, 1), 'frac_of_770': round(gbps / NVLINK_GBPS, 3)}
 
             results.append({'bucket': name, 'elements': n, 'wire': wire, 'wire_bytes': wire_bytes,
-                            'fused_peer_kernel': entry(fused_us), 'nccl_route_k1_allreduce_k2': entry(nccl_us),
+                            'fused_peer_kernel': entry(fused_us),
+                            'fused_pipelined_oneshot': entry(pipe_us) if pipe_us else None, 'nccl_route_k1_allreduce_k2': entry(nccl_us),
                             'speedup_vs_nccl_route': round(nccl_us / fused_us, 2), 'rel_diff_fused_vs_nccl': diff})
         sync.close()
     if rank == 0:

@@ -186,8 +186,10 @@ def test_fused_allreduce_sizes_and_algorithms(world):
     cases = []
     for n in (1, 7, 9, 4097, 513000):
         for wire in ('fp32', 'bf16'):
-            for algo in (1, 2):
+            for algo in (1, 2, 3):  # one-shot, two-shot, one-shot tile-pipelined (warp-specialised)
                 cases.append((f'{wire}:n{n}a{algo}', wire, algo, str(n)))
+    cases.append(('bf16:bigpipe', 'bf16', 3, str(3_963_456)))
+    cases.append(('fp32:midpipe', 'fp32', 3, str(1_000_003)))
     cases.append(('bf16:big', 'bf16', 0, str(3_963_456)))  # ResNet-18 bucket 3 (15.1 MiB fp32)
     _check(world, cases, TOL)
 
