@@ -326,7 +326,10 @@ __global__ void __launch_bounds__(kCommThreads) barrier_kernel(const __grid_cons
 
 constexpr size_t kOneshotMaxBytes = 512 * 1024;
 constexpr size_t kPipelineMinBytes = 1 << 20;  // below ~1 MB a single pack/barrier/reduce round is already latency-bound
-constexpr bool kPipelineDefault = false;       // flipped once the N=2 sweep shows it ahead (profiles/)
+// Measured on 2x B200 (profiles/r1_comm_sweep_n2_v3_pipelined.json): the warp-specialised pipeline LOSES to the phase-serial
+// kernel (98.8 vs 65.5 us at 23 MB bf16): with half the threads per role there are half as many peer loads in flight, and
+// the NVLink phase is latency x parallelism bound.  Kept as opt-in algo 3 (bit-exact, tested); not the default.
+constexpr bool kPipelineDefault = false;
 
 }  // namespace dmlb
 
