@@ -5,8 +5,7 @@ arithmetic raises.  `torch` is used by callers for device memory, streams and to
 """
 import ctypes
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, \
-    c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libdmlb.so'

@@ -198,11 +198,13 @@ int dmlb_bucket_pack_f32_bf16_tma(const float *src, uint16_t *dst, size_t n, flo
     const size_t n_tiles = n / kTileElems;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tiles) {
-        static bool configured = false;
+        static bool configured[64] = {false};  // the attribute is per device (context)
         const int smem = kTmaStages * kTileBytes;
-        if (!configured) {
+        int dev = 0;
+        DMLB_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
             DMLB_CUDA(cudaFuncSetAttribute(pack_bf16_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
         }
         const int grid = tma_grid(n_tiles);
         pack_bf16_tma_kernel<<<grid, kTmaThreads, smem, st>>>(src, dst, n_tiles, scale);
@@ -222,11 +224,13 @@ int dmlb_bucket_unpack_bf16_f32_tma(const uint16_t *src, float *dst, size_t n, f
     const size_t n_tiles = n / kTileElems;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tiles) {
-        static bool configured = false;
+        static bool configured[64] = {false};
         const int smem = kTmaStages * kTileBytesBf16 + 2 * kTileBytes;
-        if (!configured) {
+        int dev = 0;
+        DMLB_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
             DMLB_CUDA(cudaFuncSetAttribute(unpack_bf16_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
         }
         const int grid = tma_grid(n_tiles);
         unpack_bf16_tma_kernel<<<grid, kTmaThreads, smem, st>>>(src, dst, n_tiles, scale);
