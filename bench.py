@@ -237,6 +237,7 @@ def native_arm(args):
                 torch.cuda.synchronize()
                 sampler.start()
                 n0 = N.launch_count()
+                replays0 = self._graph.replays if self._graph is not None else 0
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 wall0 = time.perf_counter()
                 t0.record()
@@ -248,7 +249,9 @@ def native_arm(args):
                 dist.barrier()
                 phase.elapsed_ms = max(t0.elapsed_time(t1), 0.0)
                 phase.wall_ms = wall
-                phase.launches = N.launch_count() - n0
+                phase.launches = N.launch_count() - n0  # launched through the C ABI in the region ...
+                if self._graph is not None:                # ... plus the libdmlb kernels each graph replay re-runs
+                    phase.launches += (self._graph.replays - replays0) * self._graph.kernels_in_graph
                 phase.clocks = sampler.stop()
             sync.profile_events = False
 

@@ -86,6 +86,7 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = None
         self.replays = 0
+        self.kernels_in_graph = 0
 
     def _wire_bytes(self, n):
         return ((n + 7) // 8) * 16 if self.wire == 'bf16' else ((n + 3) // 4) * 16
@@ -149,8 +150,10 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         # capture on the very stream the warm-up steps ran on: autograd's AccumulateGrad nodes (stashed by DDP at
         # construction) then already live on the capturing stream and no cross-stream edge enters the graph
+        before = N.launch_count()
         with torch.cuda.graph(self.graph, stream=stream):
             self.loss = self._one_step()
+        self.kernels_in_graph = N.launch_count() - before  # libdmlb kernels every replay re-runs
         self.graph.replay()  # capture only records: run the step once for real
         self.replays = 1
         return self.loss
