@@ -1,12 +1,13 @@
 """Data sharding — reference dmlcloud/util/data.py, same public names, plus a device-resident shard iterator.
 
-Kept verbatim in behaviour (reference file:line):
-  shard_indices [11-30]  chunk_and_shard_indices [33-55]  shard_sequence [58-67]  sharded_xr_dataset [70-107]
-  ShardedSequenceDataset [110-147]  ShardedXrDataset [150-207]  DownstreamDataset [210-219]  PrefetchDataset [222-240]
-  BatchDataset [243-263]  interleave_batches [266-301]  interleave_dict_batches [304-341]
+Kept verbatim in behaviour (reference file:line) — the names SURVEY §8b lists for the path:
+  shard_indices [11-30]  chunk_and_shard_indices [33-55]  shard_sequence [58-67]  ShardedSequenceDataset [110-147]
+  DownstreamDataset [210-219]  PrefetchDataset [222-240]  BatchDataset [243-263]  interleave_batches [266-301]
+The xarray-specific wrappers (sharded_xr_dataset, ShardedXrDataset) and interleave_dict_batches are out of scope
+(climate-data specific, dependency absent); they are thin loops over chunk_and_shard_indices.
 The index arithmetic is integer and must be bit-exact with the reference: the shuffle goes through the very same
 third-party generator (`numpy.random.Generator(MT19937(seed))`, requirements.txt:2); oracle/shard_oracle.c restates it
-in C for the parity tests.  One fix: `interleave_*_batches(num_batches=1)` returns after passing the
+in C for the parity tests.  One fix: `interleave_batches(num_batches=1)` returns after passing the
 batches through instead of falling into the general path.
 
 New: `DeviceShardedDataset` keeps the whole uint8 dataset in HBM and produces each batch with one
@@ -65,33 +66,6 @@ def shard_sequence(
     return [sequence[i] for i in picked]
 
 
-def sharded_xr_dataset(
-    ds,
-    dim: str,
-    chunk_size: int,
-    chunk_overlap: int = 0,
-    even_shards: bool = True,
-    equal_chunks: bool = True,
-    shuffle: bool = False,
-    seed: int = 0,
-    rank: int | None = None,
-    world_size: int | None = None,
-    process_group=None,
-    load: bool = False,
-    load_kwargs: dict | None = None,
-):
-    """Chunks of an xarray Dataset/DataArray along `dim`, sharded over ranks (duck-typed: needs `ds[dim]`, `ds.isel`)."""
-    rank = dist.get_rank(process_group) if rank is None else rank
-    world_size = dist.get_world_size(process_group) if world_size is None else world_size
-    spans = chunk_and_shard_indices(len(ds[dim]), chunk_size, rank, world_size, chunk_overlap=chunk_overlap,
-                                    even_shards=even_shards, equal_chunks=equal_chunks, shuffle=shuffle, seed=seed)
-    for start, end in spans:
-        chunk = ds.isel({dim: slice(start, end)})
-        if load:
-            chunk.load(**(load_kwargs or {}))
-        yield chunk
-
-
 def _worker_adjusted(rank, world_size):
     """DataLoader workers subdivide the rank's shard (reference [131-138])."""
     info = get_worker_info()
@@ -125,48 +99,6 @@ class ShardedSequenceDataset(IterableDataset):
         rank, world_size = _worker_adjusted(self.rank, self.world_size)
         return iter(shard_sequence(self.sequence, rank, world_size, shuffle=self.shuffle, even_shards=self.even_shards,
                                    seed=self.seed + self.epoch))
-
-
-class ShardedXrDataset(IterableDataset):
-    def __init__(
-        self,
-        ds,
-        dim: str,
-        chunk_size: int,
-        chunk_overlap: int = 0,
-        even_shards: bool = True,
-        equal_chunks: bool = True,
-        shuffle: bool = False,
-        seed: int = 0,
-        rank: int | None = None,
-        world_size: int | None = None,
-        process_group=None,
-        load: bool = False,
-        load_kwargs: dict | None = None,
-    ):
-        self.ds = ds
-        self.dim = dim
-        self.chunk_size = chunk_size
-        self.chunk_overlap = chunk_overlap
-        self.even_shards = even_shards
-        self.equal_chunks = equal_chunks
-        self.shuffle = shuffle
-        self.seed = seed
-        self.load = load
-        self.load_kwargs = load_kwargs
-        self.rank = rank if rank is not None else dist.get_rank(process_group)
-        self.world_size = world_size if world_size is not None else dist.get_world_size(process_group)
-        self._num_iters = 0
-
-    def set_epoch(self, epoch: int):
-        self._num_iters = epoch
-
-    def __iter__(self):
-        rank, world_size = _worker_adjusted(self.rank, self.world_size)
-        return sharded_xr_dataset(self.ds, self.dim, self.chunk_size, chunk_overlap=self.chunk_overlap,
-                                  even_shards=self.even_shards, equal_chunks=self.equal_chunks, shuffle=self.shuffle,
-                                  seed=self.seed + self._num_iters, rank=rank, world_size=world_size, load=self.load,
-                                  load_kwargs=self.load_kwargs)
 
 
 class DownstreamDataset(IterableDataset):
@@ -248,36 +180,6 @@ def interleave_batches(iterable: Iterable[torch.Tensor], num_batches: int, pin_m
             group = []
             for out in range(num_batches):
                 yield buf[out]
-
-
-def interleave_dict_batches(iterable: Iterable[dict], num_batches: int, pin_memory: bool = False):
-    """interleave_batches for dict-of-tensor batches."""
-    if num_batches < 1:
-        raise ValueError('num_batches must be greater than 0')
-    if num_batches == 1:
-        yield from iterable
-        return
-
-    group, bufs, widths = [], {}, {}
-    for batch in iterable:
-        if not bufs:
-            for key, tensor in batch.items():
-                if tensor.shape[0] % num_batches != 0:
-                    raise ValueError(
-                        f'Batch dimension ({tensor.shape[0]}) must be divisible by num_batches={num_batches}')
-                widths[key] = tensor.shape[0] // num_batches
-                bufs[key] = torch.empty((num_batches, *tensor.shape), dtype=tensor.dtype, device=tensor.device,
-                                        pin_memory=pin_memory)
-        group.append(batch)
-        if len(group) == num_batches:
-            for key, buf in bufs.items():
-                w = widths[key]
-                for out in range(num_batches):
-                    for src in range(num_batches):
-                        buf[out, src * w:(src + 1) * w] = group[src][key][out * w:(out + 1) * w]
-            group = []
-            for out in range(num_batches):
-                yield {key: buf[out] for key, buf in bufs.items()}
 
 
 class DeviceShardedDataset:
