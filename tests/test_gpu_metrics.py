@@ -284,3 +284,69 @@ def test_metric_session_multi_rank_one_gpu(world, route):
     for r in range(world):
         ok = json.loads((out / f'ok{r}').read_text())
         assert ok['raised'] and ok['raised3'], (r, ok)
+
+
+class TestSlabEdgeCases:
+    """Rarely-hit host/device paths of the slab: growth past the initial capacity, selections fragmented into more cell
+    ranges than one launch takes, wide (many-lane) metrics, NaN propagation, every source dtype."""
+
+    def test_growth_fragmented_prefix_and_wide_metrics(self):
+        from dmlcloud_b200 import _native as N
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t = MetricTracker()
+        ops = [Reduction.MEAN, Reduction.SUM, Reduction.MIN, Reduction.MAX]
+        rng = np.random.RandomState(0)
+        vals = rng.randn(3, 3000).astype(np.float32)
+        for i in range(3000):  # 3000 cells: the slab grows 1024 -> 2048 -> 4096 while values are already folded
+            t.register_metric(f'{"a" if i % 2 else "b"}/{i}', ops[i % 4])
+            t.track(f'{"a" if i % 2 else "b"}/{i}', float(vals[0, i]))
+        wide = torch.from_numpy(rng.randn(5, 4096).astype(np.float32)).cuda()
+        t.register_metric('wide', Reduction.MAX, dim=[0])  # 4096 lanes, 5 elements folded into each per step
+        t.track('wide', wide)
+        t.track('wide', wide * 0.5)
+        for s in (1, 2):
+            for i in range(3000):
+                t.track(f'{"a" if i % 2 else "b"}/{i}', float(vals[s, i]))
+        assert t._slab.capacity >= 7096
+        t._slab.flush()  # queued host scalars go out first; what follows is the reduce alone
+        before = N.launch_count()
+        t.reduce_all(prefix='a/')  # every second metric: 1500 one-cell ranges > DMLB_MAX_RANGES -> several launches
+        assert N.launch_count() - before == -(-1500 // N.MAX_RANGES)
+        t.next_epoch()
+        for i in (0, 1, 2, 3, 1023, 1024, 2047, 2048, 2999):
+            v = vals[:, i]
+            want = [v.mean(), v.sum(), v.min(), v.max()][i % 4]
+            got = t[f'{"a" if i % 2 else "b"}/{i}'][0]
+            np.testing.assert_allclose(got.item(), want, rtol=1e-5, atol=1e-6)
+        w = t['wide'][0]
+        assert w.shape == (4096,) and torch.equal(w, torch.maximum(wide.amax(0), (wide * 0.5).amax(0)).cpu())
+
+    def test_nan_propagation_and_dtypes(self):
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t = MetricTracker()
+        t.register_metric('mn', Reduction.MIN)
+        t.register_metric('mx', Reduction.MAX)
+        for v in (1.0, float('nan'), -2.0):
+            t.track('mn', torch.tensor(v, device='cuda'))
+            t.track('mx', v)
+        cases = {
+            'f16': (torch.float16, Reduction.MEAN, [1.5, 2.5]), 'bf16': (torch.bfloat16, Reduction.SUM, [1.5, 2.5]),
+            'f64': (torch.float64, Reduction.MEAN, [1e-9, 3e-9]), 'i32': (torch.int32, Reduction.MIN, [7, -3]),
+            'u8': (torch.uint8, Reduction.MAX, [200, 13]), 'bool': (torch.bool, Reduction.SUM, [True, True]),
+            'i64': (torch.int64, Reduction.SUM, [2**40, 2**41 + 1]),
+        }
+        for name, (dt, red, vs) in cases.items():
+            t.register_metric(name, red)
+            for v in vs:
+                t.track(name, torch.tensor(v, dtype=dt, device='cuda'))
+        t.next_epoch()
+        assert torch.isnan(t['mn'][0]) and torch.isnan(t['mx'][0])  # amin / amax propagate NaN (fmin/fmax would not)
+        assert t['f16'][0].dtype == torch.float16 and t['f16'][0].item() == 2.0
+        assert t['bf16'][0].dtype == torch.bfloat16 and t['bf16'][0].item() == 4.0
+        assert t['f64'][0].dtype == torch.float64 and t['f64'][0].item() == 2e-9
+        assert t['i32'][0].dtype == torch.int32 and t['i32'][0].item() == -3
+        assert t['u8'][0].dtype == torch.uint8 and t['u8'][0].item() == 200
+        assert t['bool'][0].dtype == torch.int64 and t['bool'][0].item() == 2
+        assert t['i64'][0].item() == 2**40 + 2**41 + 1  # exact in int64 (fp64 would already round here... not, but fp32 would)
