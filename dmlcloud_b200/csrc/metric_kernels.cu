@@ -276,10 +276,7 @@ metric_reduce_kernel(const __grid_constant__ CommDev c, bool has_comm, uint64_t 
             out_flag[cell] = n > 0 ? 0 : 1;
         }
     }
-    if (!exchange) {
-        if (threadIdx.x == 0) status[blockIdx.x] = DMLB_METRIC_OK;
-        return;
-    }
+    if (!exchange) return;  // nothing can go wrong locally: the slot keeps whatever this reduce has recorded so far
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         rec_mine[0] = layout_hash;
         rec_mine[1] = (uint64_t)n_sel;
@@ -310,10 +307,11 @@ metric_reduce_kernel(const __grid_constant__ CommDev c, bool has_comm, uint64_t 
         out_val[cell] = out;
         out_flag[cell] = flag;
     }
-    // one status slot per CTA (DMLB_METRIC_STATUS_SLOTS of them): no memset before the launch, no atomics
-    st = __syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE) ? DMLB_METRIC_SPLIT_VOTE
-                                                         : (__syncthreads_or(st == DMLB_METRIC_LAYOUT) ? DMLB_METRIC_LAYOUT : DMLB_METRIC_OK);
-    if (threadIdx.x == 0) status[blockIdx.x] = st;
+    // One status slot per CTA (DMLB_METRIC_STATUS_SLOTS of them), no atomics.  Slots are sticky (max with what is there)
+    // so that a reduce split over several launches keeps an error of an earlier launch; the caller zeroes them per reduce.
+    st = __syncthreads_or(st == DMLB_METRIC_LAYOUT) ? DMLB_METRIC_LAYOUT
+                                                     : (__syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE) ? DMLB_METRIC_SPLIT_VOTE : DMLB_METRIC_OK);
+    if (threadIdx.x == 0 && st != DMLB_METRIC_OK && st > status[blockIdx.x]) status[blockIdx.x] = st;  // clean run: untouched
     comm_end(c, s);
 }
 
@@ -364,9 +362,9 @@ metric_combine_kernel(const uint64_t *__restrict__ gathered, int world, int rank
         out_val[cell] = out;
         out_flag[cell] = flag;
     }
-    st = __syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE) ? DMLB_METRIC_SPLIT_VOTE
-                                                         : (__syncthreads_or(st == DMLB_METRIC_LAYOUT) ? DMLB_METRIC_LAYOUT : DMLB_METRIC_OK);
-    if (threadIdx.x == 0) status[blockIdx.x] = st;
+    st = __syncthreads_or(st == DMLB_METRIC_LAYOUT) ? DMLB_METRIC_LAYOUT
+                                                     : (__syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE) ? DMLB_METRIC_SPLIT_VOTE : DMLB_METRIC_OK);
+    if (threadIdx.x == 0 && st != DMLB_METRIC_OK && st > status[blockIdx.x]) status[blockIdx.x] = st;  // clean run: untouched
 }
 
 static int fill_ranges(RangeParams &R, const dmlb_range *ranges, int n_ranges, int n_cells, int &n_sel) {

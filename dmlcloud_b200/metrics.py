@@ -317,6 +317,8 @@ class DeviceSlab:
             if dptr is not None:
                 base = dptr  # the kernel writes its results straight into mapped pinned host memory
         status_ptr, val_ptr, flag_ptr = base, base + STATUS_BYTES, base + STATUS_BYTES + 8 * self.capacity
+        if base == out_p:  # device-resident block: clear the sticky status slots (pooled host blocks are handed out zeroed)
+            N.check(lib.dmlb_memset_async(status_ptr, 0, STATUS_BYTES, st), 'memset(status)')
 
         def launch(comm_handle, ranges):
             # > DMLB_MAX_RANGES fragments (pathological prefix selections) take several launches

@@ -185,8 +185,9 @@ typedef struct {
     int32_t begin, end; /* cell range [begin, end) selected for this reduce */
 } dmlb_range;
 #define DMLB_MAX_RANGES 64
-/* status: DMLB_METRIC_STATUS_SLOTS int32 slots; every CTA of a reduce / combine launch writes its own slot (slot i < grid),
- * the caller zero-fills the block once at allocation and takes the maximum — no memset per launch, no atomics. */
+/* status: DMLB_METRIC_STATUS_SLOTS int32 slots; every CTA of a reduce / combine launch raises its own slot (slot i < grid) to
+ * the worst condition it saw (sticky: max with the slot's content, no atomics).  The caller zero-fills the block before a
+ * reduce (which may take several launches) and takes the maximum over the slots afterwards. */
 #define DMLB_METRIC_STATUS_SLOTS 32
 #define DMLB_METRIC_OK 0
 #define DMLB_METRIC_SPLIT_VOTE 1 /* some ranks tracked values and some did not (metrics.py:127-128) */

@@ -350,3 +350,42 @@ class TestSlabEdgeCases:
         assert t['u8'][0].dtype == torch.uint8 and t['u8'][0].item() == 200
         assert t['bool'][0].dtype == torch.int64 and t['bool'][0].item() == 2
         assert t['i64'][0].item() == 2**40 + 2**41 + 1  # exact in int64 (fp64 would already round here... not, but fp32 would)
+
+    def test_status_slots_are_sticky_within_one_reduce(self):
+        """A reduce may take several launches that share one status block: an error an earlier launch recorded must
+        survive a later clean launch (C ABI: finalize -> combine of fabricated 2-rank records)."""
+        from dmlcloud_b200 import _native as N
+        from dmlcloud_b200.metrics import STATUS_BYTES, DeviceSlab, Reduction, _desc_word
+
+        slab = DeviceSlab(torch.device('cuda', 0))
+        lib, st = slab._lib(), N.stream_ptr()
+        cell = slab.alloc(1, _desc_word(Reduction.SUM, torch.float32, True))
+        arr = (N.Range * 1)(N.Range(cell, cell + 1))
+        words = int(lib.dmlb_metric_record_words(1))
+
+        def record():
+            rec = torch.empty(words, dtype=torch.int64, device='cuda')
+            N.check(lib.dmlb_metric_finalize(slab.acc.data_ptr(), slab.cnt.data_ptr(), slab.desc.data_ptr(), arr, 1, 77, 0,
+                                             rec.data_ptr(), st), 'finalize')
+            return rec
+
+        empty = record()  # nothing tracked yet: count 0
+        slab.fold_imm(cell, 2.5, False)
+        slab.flush()
+        full = record()
+        out = torch.zeros(STATUS_BYTES + 9 * slab.capacity, dtype=torch.uint8, device='cuda')
+        base = out.data_ptr()
+
+        def combine(a, b):
+            gathered = torch.cat([a, b])
+            N.check(lib.dmlb_metric_combine(gathered.data_ptr(), 2, 0, slab.desc.data_ptr(), arr, 1,
+                                            base + STATUS_BYTES, base + STATUS_BYTES + 8 * slab.capacity, base, st), 'combine')
+            torch.cuda.synchronize()
+            return int(out[:STATUS_BYTES].view(torch.int32).max())
+
+        assert combine(full, full) == N.METRIC_OK
+        assert out[STATUS_BYTES:STATUS_BYTES + 8 * slab.capacity].view(torch.float64)[cell].item() == 5.0
+        assert combine(full, empty) == N.METRIC_SPLIT_VOTE
+        assert combine(full, full) == N.METRIC_SPLIT_VOTE  # sticky until the caller clears the block
+        out[:STATUS_BYTES].zero_()
+        assert combine(full, full) == N.METRIC_OK
