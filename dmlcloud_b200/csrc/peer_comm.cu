@@ -15,6 +15,7 @@
 // Numerics: fp32 accumulate in rank order 0..W-1 on every rank => results are bit-identical across ranks and equal to
 // oracle/grad_oracle.py allreduce_f32 / allreduce_bf16.  Two-shot with the bf16 wire rounds the sum to bf16 for the
 // all-gather phase (same as an NCCL bf16 all-reduce); the fp32 wire is exact in both algorithms.
+#include <cstdlib>
 #include <new>
 
 #include "peer_comm.cuh"
@@ -258,7 +259,10 @@ allreduce_oneshot_pipelined_kernel(const __grid_constant__ CommDev c, float *buc
 // two-shot: slice q (S wire vectors) is reduced by rank q.  CTA b owns vector range [b*per, (b+1)*per) of EVERY slice,
 // so it only ever depends on what the peers' CTA b wrote (per-CTA barriers suffice).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kWire, int kU>
+// kPush: the all-gather half is PUSHED — the rank that reduced a slice stores it into every rank's result half (posted
+// NVLink writes that overlap the reduce-scatter's pulls, which use the other link direction), and after the second
+// barrier every rank widens from its LOCAL copy at HBM speed.  !kPush: peers pull the slices after the second barrier.
+template <int kWire, int kU, bool kPush>
 __global__ void __launch_bounds__(kCommThreads, 2)
 allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S, float scale,
                          double *sumsq_out) {
@@ -279,26 +283,38 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     }
     comm_barrier(c, 0, s);
 
-    // phase 2 (reduce-scatter): I reduce slice `rank` from every peer's staging into my result half
+    // phase 2 (reduce-scatter): I reduce slice `rank` from every peer's staging — into my result half (pull variant:
+    // slice-local index) or into every rank's result half (push variant: global vector index)
+    constexpr int kMaxW = DMLB_MAX_WORLD / kU;
     {
         uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
         const size_t off = (size_t)c.rank * S;
         const size_t lim = off < nvec ? min(hi, nvec - off) : 0;
-        if (lo < lim)
-            reduce_range<kWire, kU>(c, half, lo, lim, off, [&](size_t i, const float *acc) { res[i] = W::pack(acc); });
+        if (lo < lim) {
+            if (kPush)
+                reduce_range<kWire, kU>(c, half, lo, lim, off, [&](size_t i, const float *acc) {
+                    const uint4 v = W::pack(acc);
+#pragma unroll
+                    for (int r = 0; r < kMaxW; ++r)
+                        if (r < c.world) reinterpret_cast<uint4 *>(c.result(r, half))[off + i] = v;
+                });
+            else
+                reduce_range<kWire, kU>(c, half, lo, lim, off, [&](size_t i, const float *acc) { res[i] = W::pack(acc); });
+        }
     }
     comm_barrier(c, 1, s);
 
-    // phase 3 (all-gather + K2): pull every rank's reduced slice (W loads in flight per thread) and widen into the bucket
+    // phase 3 (all-gather + K2): W loads in flight per thread — from every rank's reduced slice over NVLink (pull) or
+    // from this rank's own, already complete, result half (push) — widened into the bucket
     double part = 0.0;
     const bool want_sumsq = sumsq_out != nullptr;
-    constexpr int kMaxW = DMLB_MAX_WORLD / kU;
     for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
         uint4 w[kMaxW];
 #pragma unroll
         for (int q = 0; q < kMaxW; ++q)
             if (q < c.world && (size_t)q * S + i < nvec)
-                w[q] = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
+                w[q] = kPush ? ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(c.rank, half)) + (size_t)q * S + i)
+                             : ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
 #pragma unroll
         for (int q = 0; q < kMaxW; ++q) {
             const size_t g = (size_t)q * S + i;
@@ -318,6 +334,232 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     comm_end(c, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// two-shot, PUSH-pipelined (algo 5).  Every NVLink transfer is a posted store, every load is local:
+//
+//   A(t)  pack chunk t of every slice q and store it into rank q's staging half at [my rank][i]      (scatter push)
+//   B(t)  sum the W contributions of my slice's chunk t from my LOCAL staging half (rank order), cast,
+//         store the reduced vectors into every rank's result half at the global index                 (gather push)
+//   C(t)  widen chunk t of every slice from my LOCAL result half into the fp32 bucket (+ sum of squares)
+//
+// A thread never waits for an NVLink round trip: peer loads (the latency x parallelism limit of the pull kernels) are
+// gone, and the links stay busy while the HBM passes run.  The six worker warps of a CTA run A(t), B(t-1), C(t-2)
+// back to back; two control warps (one for stage A, one for stage B) do all the signalling so that the system-scope
+// fence before a flag store (which waits for the pushes to be acknowledged) never stalls a worker:
+//   workers  -> control : shared-memory arrival counter per stage (release: __syncwarp + fence.cta + atomicAdd)
+//   control  -> peers   : fence.sys + st.release.sys of (s << 8 | t + 1) into flag region 2 (A) / 3 (B), per CTA
+//   peers    -> control : ld.acquire.sys polling of this CTA's own flag words
+//   control  -> workers : shared-memory "chunks ready" counter per stage
+// WAR safety is the double buffer again: a peer can only be in collective s+1 (writing the other half of my arena)
+// once all my CTAs have finished stages A and B of s, and it cannot finish s+1 before I have taken part in it.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kCtrlWarps = 2;
+constexpr int kWorkerWarps = kCommThreads / 32 - kCtrlWarps;
+constexpr int kWorkers = kWorkerWarps * 32;
+
+struct PushShared {
+    uint32_t done[2];   // worker warps that finished stage X of (done / kWorkerWarps) chunks
+    uint32_t ready[2];  // chunks of stage X whose data from every rank has landed in this rank's arena
+};
+
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+
+template <int kWire, int kU>
+__global__ void __launch_bounds__(kCommThreads, 2)
+allreduce_push_pipelined_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S,
+                                size_t chunk, float scale, double *sumsq_out) {
+    typedef Wire<kWire> W;
+    constexpr int E = W::kElems;
+    constexpr int kMaxW = DMLB_MAX_WORLD / kU;
+    constexpr int kUA = 16 / E;  // wire vectors per worker thread per iteration of stages A and C: four 128-bit bucket loads in flight
+    __shared__ PushShared sh;
+    __shared__ double s_red[kWorkerWarps];
+    if (threadIdx.x == 0) sh.done[0] = sh.done[1] = sh.ready[0] = sh.ready[1] = 0u;
+    const uint32_t s = comm_begin(c);  // (contains the __syncthreads that publishes the zeroed counters)
+    const int half = s & 1;
+    const size_t per = (S + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = min(S, lo + per);
+    const int K = hi > lo ? (int)((hi - lo + chunk - 1) / chunk) : 0;
+    const uint32_t base = s << 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double part = 0.0;
+
+    if (warp < kCtrlWarps) {
+        // ---- control warp of stage X: lane r talks to rank r ----
+        const int X = warp;
+        const int region = 2 + X;
+        int sig = 0, rdy = 0;
+        const unsigned long long t0 = globaltimer_ns();
+        while (sig < K || rdy < K) {
+            if (sig < K) {
+                uint32_t d = 0;
+                if (lane == 0) {
+                    d = ld_volatile_shared(&sh.done[X]);
+                    __threadfence_block();
+                }
+                d = __shfl_sync(0xffffffffu, d, 0);
+                __syncwarp();
+                if (d >= (uint32_t)kWorkerWarps * (uint32_t)(sig + 1)) {  // every worker warp has issued chunk `sig`
+                    if (lane < c.world) {
+                        __threadfence_system();  // cumulative: the workers' pushes are ordered before the flag
+                        st_release_sys(c.flags(lane, region, blockIdx.x) + c.rank, base + (uint32_t)sig + 1u);
+                    }
+                    ++sig;
+                }
+            }
+            if (rdy < K) {
+                bool ok = true;
+                if (lane < c.world)
+                    ok = (int32_t)(ld_acquire_sys(c.flags(c.rank, region, blockIdx.x) + lane) - (base + (uint32_t)rdy + 1u)) >= 0;
+                if (__all_sync(0xffffffffu, ok)) {
+                    __syncwarp();
+                    ++rdy;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        *reinterpret_cast<volatile uint32_t *>(&sh.ready[X]) = (uint32_t)rdy;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > c.timeout_ns)) {  // a peer died: record it, release the workers, stop
+                if (lane == 0) {
+                    atomicExch(c.err(), 1u);
+                    *reinterpret_cast<volatile uint32_t *>(&sh.ready[X]) = (uint32_t)K;
+                }
+                break;
+            }
+        }
+    } else {
+        const int w = threadIdx.x - kCtrlWarps * 32;
+        const bool want_sumsq = sumsq_out != nullptr;
+        const uint4 *my_stage = reinterpret_cast<const uint4 *>(c.stage(c.rank, half));
+        const uint4 *my_result = reinterpret_cast<const uint4 *>(c.result(c.rank, half));
+        auto arrive = [&](int X) {
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&sh.done[X], 1u);
+            }
+        };
+        auto await = [&](int X, int chunks) {
+            if (lane == 0)
+                while (ld_volatile_shared(&sh.ready[X]) < (uint32_t)chunks) {}
+            __syncwarp();
+            __threadfence_block();
+        };
+        for (int t = 0; t < K + 2; ++t) {
+            if (t < K) {  // ---- A(t): scale + cast, scatter to the slice owners ----
+                const size_t clo = lo + (size_t)t * chunk;
+                const uint32_t cw = (uint32_t)(min(hi, clo + chunk) - clo);
+                const uint32_t items = cw * (uint32_t)c.world;
+                for (uint32_t j0 = w; j0 < items; j0 += kWorkers * kUA) {
+                    float v[kUA][E];
+                    size_t idx[kUA];
+                    int owner[kUA];
+#pragma unroll
+                    for (int u = 0; u < kUA; ++u) {
+                        const uint32_t j = j0 + u * kWorkers;
+                        owner[u] = -1;
+                        if (j < items) {
+                            const uint32_t q = j / cw;
+                            const size_t i = clo + (j - q * cw);
+                            const size_t g = (size_t)q * S + i;
+                            if (g < nvec) {
+                                owner[u] = (int)q;
+                                idx[u] = (size_t)c.rank * S + i;
+                                load_bucket<E>(bucket, g, n, scale, v[u]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUA; ++u)
+                        if (owner[u] >= 0) reinterpret_cast<uint4 *>(c.stage(owner[u], half))[idx[u]] = W::pack(v[u]);
+                }
+                arrive(0);
+            }
+            if (t >= 1 && t - 1 < K) {  // ---- B(t-1): reduce my slice's chunk locally, push it to everyone ----
+                await(0, t);
+                const size_t clo = lo + (size_t)(t - 1) * chunk;
+                const size_t chi = min(hi, clo + chunk);
+                const size_t off = (size_t)c.rank * S;
+                const size_t lim = off < nvec ? min(chi, nvec - off) : 0;
+                for (size_t i0 = clo + w; i0 < lim; i0 += (size_t)kWorkers * kU) {
+                    uint4 x[kU][kMaxW];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const size_t i = i0 + (size_t)u * kWorkers;
+                        if (i < lim) {
+#pragma unroll
+                            for (int r = 0; r < kMaxW; ++r)
+                                if (r < c.world) x[u][r] = ld_coherent_u4(my_stage + (size_t)r * S + i);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const size_t i = i0 + (size_t)u * kWorkers;
+                        if (i < lim) {
+                            float acc[E];
+#pragma unroll
+                            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+#pragma unroll
+                            for (int r = 0; r < kMaxW; ++r)
+                                if (r < c.world) W::accumulate(acc, x[u][r]);
+                            const uint4 red = W::pack(acc);
+#pragma unroll
+                            for (int r = 0; r < kMaxW; ++r)
+                                if (r < c.world) reinterpret_cast<uint4 *>(c.result(r, half))[off + i] = red;
+                        }
+                    }
+                }
+                arrive(1);
+            }
+            if (t >= 2) {  // ---- C(t-2): widen every slice's chunk from my local result half ----
+                await(1, t - 1);
+                const size_t clo = lo + (size_t)(t - 2) * chunk;
+                const uint32_t cw = (uint32_t)(min(hi, clo + chunk) - clo);
+                const uint32_t items = cw * (uint32_t)c.world;
+                for (uint32_t j0 = w; j0 < items; j0 += kWorkers * kUA) {
+                    uint4 x[kUA];
+                    size_t gi[kUA];
+#pragma unroll
+                    for (int u = 0; u < kUA; ++u) {
+                        const uint32_t j = j0 + u * kWorkers;
+                        gi[u] = nvec;
+                        if (j < items) {
+                            const uint32_t q = j / cw;
+                            const size_t g = (size_t)q * S + clo + (j - q * cw);
+                            if (g < nvec) {
+                                gi[u] = g;
+                                x[u] = ld_coherent_u4(my_result + g);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUA; ++u)
+                        if (gi[u] < nvec) {
+                            float acc[E];
+#pragma unroll
+                            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+                            W::accumulate(acc, x[u]);
+                            part += store_bucket<E>(bucket, gi[u], n, acc, want_sumsq);
+                        }
+                }
+            }
+        }
+        if (want_sumsq) {
+            part = warp_sum(part);
+            if (lane == 0) s_red[warp - kCtrlWarps] = part;
+        }
+    }
+    __syncthreads();
+    if (sumsq_out && threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < kWorkerWarps; ++i) tot += s_red[i];
+        if (tot != 0.0) atomicAdd(sumsq_out, tot);
+    }
+    comm_end(c, s);
+}
+
 __global__ void __launch_bounds__(kCommThreads) barrier_kernel(const __grid_constant__ CommDev c) {
     const uint32_t s = comm_begin(c);
     comm_barrier(c, 0, s);
@@ -330,6 +572,18 @@ constexpr size_t kPipelineMinBytes = 1 << 20;  // below ~1 MB a single pack/barr
 // kernel (98.8 vs 65.5 us at 23 MB bf16): with half the threads per role there are half as many peer loads in flight, and
 // the NVLink phase is latency x parallelism bound.  Kept as opt-in algo 3 (bit-exact, tested); not the default.
 constexpr bool kPipelineDefault = false;
+// two-shot all-gather half: pushed by the reducing rank (algo 4) or pulled by the consumers (algo 2)
+constexpr bool kPushDefault = false;
+
+// vectors (all slices together) one CTA moves per pipeline step of algo 5; DMLB_PUSH_STEP_VECTORS overrides it for tuning
+static size_t push_step_vectors() {
+    static size_t value = [] {
+        const char *e = getenv("DMLB_PUSH_STEP_VECTORS");
+        long v = e ? atol(e) : 0;
+        return (size_t)(v >= 8 ? v : 1536);
+    }();
+    return value;
+}
 
 }  // namespace dmlb
 
@@ -401,7 +655,34 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
 #undef DMLB_LAUNCH_PIPE
         return launched();
     }
+    if (algo == 5) {
+        const int W = c->dev.world;
+        const size_t S = (nvec + W - 1) / W;
+        if ((size_t)W * S * 16 > c->dev.msg_cap) return DMLB_ECAPACITY;  // the owner's staging half holds W x S vectors
+        size_t chunk = push_step_vectors() / W;  // vectors of ONE slice per pipeline step
+        if (chunk < 1) chunk = 1;
+        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
+        size_t want = (S + chunk - 1) / chunk;
+        if (want > cap) want = cap;
+        const int grid = (int)(want < 1 ? 1 : want);
+        const size_t per = (S + grid - 1) / grid;
+        if ((per + chunk - 1) / chunk > 250) chunk = (per + 249) / 250;  // chunk index must fit the flag's low 8 bits
+#define DMLB_LAUNCH_PUSH(WIRE, U) \
+    allreduce_push_pipelined_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, S, chunk, scale, sumsq)
+        if (wire == DMLB_WIRE_BF16) {
+            if (W <= 2) DMLB_LAUNCH_PUSH(DMLB_WIRE_BF16, 4);
+            else if (W <= 4) DMLB_LAUNCH_PUSH(DMLB_WIRE_BF16, 2);
+            else DMLB_LAUNCH_PUSH(DMLB_WIRE_BF16, 1);
+        } else {
+            if (W <= 2) DMLB_LAUNCH_PUSH(DMLB_WIRE_F32, 4);
+            else if (W <= 4) DMLB_LAUNCH_PUSH(DMLB_WIRE_F32, 2);
+            else DMLB_LAUNCH_PUSH(DMLB_WIRE_F32, 1);
+        }
+#undef DMLB_LAUNCH_PUSH
+        return launched();
+    }
     const bool oneshot = algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || c->dev.world <= 2));
+    const bool push = algo == 4 || (algo == 0 && kPushDefault);
     const int W = c->dev.world;
     const int kU = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
     const size_t items = oneshot ? nvec : (nvec + W - 1) / W;  // vectors a CTA grid is spread over
@@ -413,9 +694,12 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
     do {                                                                                                              \
         if (oneshot)                                                                                                  \
             allreduce_oneshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);  \
+        else if (push)                                                                                                \
+            allreduce_twoshot_kernel<WIRE, U, true><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,   \
+                                                                                   scale, sumsq);                     \
         else                                                                                                          \
-            allreduce_twoshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items, scale,  \
-                                                                             sumsq);                                  \
+            allreduce_twoshot_kernel<WIRE, U, false><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,  \
+                                                                                    scale, sumsq);                    \
     } while (0)
     if (wire == DMLB_WIRE_BF16) {
         if (kU == 4) DMLB_LAUNCH_AR(DMLB_WIRE_BF16, 4);

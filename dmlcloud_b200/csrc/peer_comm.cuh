@@ -3,7 +3,7 @@
 // Every rank owns one ARENA (cudaMalloc, exported with CUDA IPC, mapped by all peers over NVLink 5 / NVSwitch):
 //
 //   [0      ..  4 KB)   control: seq (u32), done counter (u32), error word (u32)      — touched only by the owner
-//   [4 KB   .. 64 KB)   flags[3 regions][kMaxCtas][8 ranks] u32                       — written by peers, read by owner
+//   [4 KB   .. 64 KB)   flags[4 regions][kMaxCtas][8 ranks] u32                       — written by peers, read by owner
 //   [64 KB  .. +2*M )   stage[2 halves][M bytes]    this rank's scaled/cast message   — read by peers
 //   [ ...   .. +2*M )   result[2 halves][M bytes]   two-shot: this rank's reduced slice — read by peers
 //
@@ -23,7 +23,7 @@ namespace dmlb {
 
 constexpr int kMaxCtas = 296;  // 2 per SM on 148 SMs
 constexpr size_t kCtrlBytes = 4096;
-constexpr int kFlagRegions = 3;  // 0, 1: the per-collective barriers; 2: per-chunk flags of the pipelined all-reduce
+constexpr int kFlagRegions = 4;  // 0, 1: the per-collective barriers; 2, 3: per-chunk flags of the pipelined all-reduces
 constexpr size_t kFlagBytes = (size_t)kFlagRegions * kMaxCtas * DMLB_MAX_WORLD * sizeof(uint32_t);
 constexpr size_t kHeaderBytes = 65536;
 static_assert(kCtrlBytes + kFlagBytes <= kHeaderBytes, "arena header");

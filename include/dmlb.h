@@ -137,8 +137,10 @@ size_t dmlb_comm_arena_bytes(size_t max_message_bytes);
 int dmlb_comm_create(void **comm, int world, int rank, void *const *arenas, size_t max_message_bytes);
 int dmlb_comm_destroy(void *comm);
 /* in-place averaged all-reduce of an fp32 bucket: bucket = sum_r wire(bucket_r * scale)  (scale = 1/W).
- * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot, 3 one-shot tile-pipelined (pack warps
- * and reduce warps of a CTA work on different chunks at the same time; per-chunk flags). */
+ * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot (reduced slices pulled by the peers),
+ * 3 one-shot tile-pipelined (pack warps and reduce warps of a CTA work on different chunks at the same time; per-chunk
+ * flags), 4 two-shot with the reduced slices pushed into every peer's arena by the rank that reduced them, 5 two-shot
+ * push-pipelined (scatter and gather both as posted peer stores, chunked, control warps do the signalling). */
 int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float scale, double *sumsq, int algo,
                         void *stream);
 /* one flag barrier across all ranks on `stream` (setup / tests) */

@@ -5,6 +5,9 @@
 For every size (the MNIST bucket, the three ResNet-18 DDP buckets, the whole ResNet-18 gradient set) and wire dtype:
   fused   dmlb_comm_allreduce: scale+cast -> peer exchange -> sum -> write-back in ONE kernel.  R launches are captured
           into a CUDA graph and the replay is timed with CUDA events (device time, no host launch latency), max over ranks.
+          Besides the default dispatch (algo 0), messages >= 1 MB are also timed with the two-shot algorithm forced, in
+          its pull (algo 2) and push (algo 4) variants and with the all-push chunk-pipelined kernel (algo 5; its step
+          size comes from DMLB_PUSH_STEP_VECTORS, recorded in the output).
   nccl    what the NCCL route costs for the same result: K1 pack (libdmlb) -> ncclAllReduce (torch.distributed) -> K2
           unpack (libdmlb), timed with CUDA events around 20 back-to-back iterations, max over ranks.
 Reported per entry: microseconds, algorithmic bus bandwidth 2(W-1)/W * wire_bytes / time (GB/s) and its fraction of the
@@ -25,6 +28,8 @@ from dmlcloud_b200.gradsync import WIRES, GradBucketSync  # noqa: E402
 from dmlcloud_b200.util import distributed as D  # noqa: E402
 
 NVLINK_GBPS = 770.0
+PIPELINED = os.environ.get('SWEEP_PIPELINED', '0') == '1'  # algo 3: measured slower in round 1, off by default
+PUSH_PIPELINED = os.environ.get('SWEEP_PUSH_PIPELINED', '1') == '1'  # algo 5
 SIZES = [('mnist_cnn', 10_330), ('resnet18_b0', 513_000), ('resnet18_b2', 3_963_456), ('resnet18_b1', 7_213_056),
          ('resnet18_all', 11_689_512)]
 
@@ -53,52 +58,42 @@ def main():
             base = torch.randn(n, generator=g).to(dev)
             buf = base.clone()
             wire_bytes = n * (2 if wire == 'bf16' else 4)
-            # ---- fused peer kernel, graph-timed ----
+            # ---- fused peer kernel, graph-timed: R launches captured back to back, replay timed with CUDA events ----
             R = 10
-            with torch.cuda.stream(side):
-                st = N.stream_ptr(side)
-                N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0 / world, None, 0, st))
-                torch.cuda.synchronize()
-                fused_result = buf.clone()
-                graph = torch.cuda.CUDAGraph()
-                dist.barrier()
-                with torch.cuda.graph(graph, stream=side):
-                    for _ in range(R):
-                        N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, 0,
-                                                        N.stream_ptr(side)))
-                times = []
-                for _ in range(6):
-                    dist.barrier()
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    graph.replay()
-                    b.record()
-                    b.synchronize()
-                    times.append(a.elapsed_time(b) * 1e3 / R)
-            fused_us = gather_max(statistics.median(times[1:]))
-            # ---- tile-pipelined one-shot (algo 3), same timing method ----
-            pipe_us = None
-            if wire_bytes >= (1 << 20):
+
+            def time_algo(algo):
                 with torch.cuda.stream(side):
-                    g3 = torch.cuda.CUDAGraph()
-                    N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, 3,
-                                                    N.stream_ptr(side)))
+                    st = N.stream_ptr(side)
+                    N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, algo, st))
                     torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
                     dist.barrier()
-                    with torch.cuda.graph(g3, stream=side):
+                    with torch.cuda.graph(graph, stream=side):
                         for _ in range(R):
-                            N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, 3,
-                                                            N.stream_ptr(side)))
-                    t3 = []
+                            N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None,
+                                                            algo, N.stream_ptr(side)))
+                    times = []
                     for _ in range(6):
                         dist.barrier()
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record()
-                        g3.replay()
+                        graph.replay()
                         b.record()
                         b.synchronize()
-                        t3.append(a.elapsed_time(b) * 1e3 / R)
-                pipe_us = gather_max(statistics.median(t3[1:]))
+                        times.append(a.elapsed_time(b) * 1e3 / R)
+                return gather_max(statistics.median(times[1:]))
+
+            with torch.cuda.stream(side):
+                N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0 / world, None, 0,
+                                                N.stream_ptr(side)))
+                torch.cuda.synchronize()
+                fused_result = buf.clone()
+            fused_us = time_algo(0)
+            big = wire_bytes >= (1 << 20)
+            pipe_us = time_algo(3) if big and PIPELINED else None  # tile-pipelined one-shot (algo 3)
+            pull_us = time_algo(2) if big else None                # two-shot, reduced slices pulled by the peers
+            push_us = time_algo(4) if big else None                # two-shot, reduced slices pushed by the reducer
+            ppipe_us = time_algo(5) if big and PUSH_PIPELINED else None  # two-shot, all-push, chunk-pipelined (control warps)
             # ---- NCCL route ----
             buf2 = base.clone()
             stage = torch.empty(n, dtype=torch.bfloat16, device=dev) if wire == 'bf16' else None
@@ -136,11 +131,16 @@ def main():
 
             results.append({'bucket': name, 'elements': n, 'wire': wire, 'wire_bytes': wire_bytes,
                             'fused_peer_kernel': entry(fused_us),
-                            'fused_pipelined_oneshot': entry(pipe_us) if pipe_us else None, 'nccl_route_k1_allreduce_k2': entry(nccl_us),
+                            'fused_pipelined_oneshot': entry(pipe_us) if pipe_us else None,
+                            'twoshot_pull_forced': entry(pull_us) if pull_us else None,
+                            'twoshot_push_forced': entry(push_us) if push_us else None,
+                            'push_pipelined_forced': entry(ppipe_us) if ppipe_us else None,
+                            'nccl_route_k1_allreduce_k2': entry(nccl_us),
                             'speedup_vs_nccl_route': round(nccl_us / fused_us, 2), 'rel_diff_fused_vs_nccl': diff})
         sync.close()
     if rank == 0:
-        print(json.dumps({'world': world, 'gpu': torch.cuda.get_device_name(dev), 'results': results}, indent=1), file=out,
+        print(json.dumps({'world': world, 'gpu': torch.cuda.get_device_name(dev),
+                          'push_step_vectors': int(os.environ.get('DMLB_PUSH_STEP_VECTORS', '1536')), 'results': results}, indent=1), file=out,
               flush=True)
     dist.barrier()
     dist.destroy_process_group()
