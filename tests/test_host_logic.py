@@ -165,6 +165,42 @@ class TestTrackerHostLogic:
         assert t['x'][0].item() == 2.5
         assert isinstance(t._histories['x'][0], torch.Tensor)
 
+    def test_deferred_results_of_several_epochs_and_shapes(self):
+        """Four epochs reduced without anyone looking (deferred): every epoch's entry is still pending, scalar metrics
+        are decoded through the once-per-reduce bulk conversion, wide / never-tracked / plain metrics through the
+        general path; a later state_dict round trip sees plain values only."""
+        from dmlcloud_b200.metrics import MetricTracker, Reduction, _Deferred
+
+        t = make_tracker()
+        t.deferred = True
+        for i in range(6):
+            t.register_metric(f's{i}', Reduction.MEAN if i % 2 else Reduction.SUM)
+        t.register_metric('wide', Reduction.MAX, dim=[0])
+        t.register_metric('never', Reduction.SUM)
+        t.register_metric('count', Reduction.SUM)
+        t.register_metric('plain')
+        for e in range(4):
+            for i in range(6):
+                t.track(f's{i}', float(i + e))
+                t.track(f's{i}', float(i))
+            t.track('wide', torch.arange(6.0).reshape(2, 3) + e)
+            t.track('count', 3)
+            t.track('count', 4)
+            t.track('plain', e)
+            t.next_epoch()
+        assert all(isinstance(x, _Deferred) for x in t._histories['s3']) and len(t._deferred_slots) == 4 * 9  # 6 scalars, wide, count + the emptiness vote carried by 'never'
+        assert [x.item() for x in t['s3']] == [3.0, 3.5, 4.0, 4.5]
+        assert [x.item() for x in t['s4']] == [8.0, 9.0, 10.0, 11.0]
+        assert all(x.dtype == torch.float32 and x.shape == () for x in t['s3'])
+        assert [x.tolist() for x in t['wide']] == [[3.0 + e, 4.0 + e, 5.0 + e] for e in range(4)]
+        assert t['never'] == [None] * 4 and t['plain'] == [0, 1, 2, 3]
+        assert [x.item() for x in t['count']] == [7] * 4 and t['count'][0].dtype == torch.int64
+        assert not t._deferred_slots
+        t2 = MetricTracker()
+        t2.bind(slab=OracleSlab())
+        t2.load_state_dict(t.state_dict())
+        assert [x.item() for x in t2['s4']] == [8.0, 9.0, 10.0, 11.0]
+
     def test_one_launch_per_reduce_all(self):
         from dmlcloud_b200.metrics import Reduction
 
