@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument('--metric-route', choices=['auto', 'peer', 'collective'], default='auto')
     ap.add_argument('--no-graph', action='store_true', help='eager step loop instead of the whole-step CUDA graph')
     ap.add_argument('--no-fused-adam', action='store_true', help='torch.optim.Adam(fused=False)')
+    ap.add_argument('--flat-adam', action='store_true',
+                    help='dmlcloud_b200.optim.FlatAdam (libdmlb K5: one launch over flat buffers) instead of torch.optim.Adam')
     ap.add_argument('--channels-last', action='store_true', help='keep model + images in NHWC (cuDNN bf16 native layout)')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -183,9 +185,14 @@ def native_arm(args):
             if args.channels_last:
                 model = model.to(memory_format=torch.channels_last)
             self.pipeline.register_model('cnn', model, verbose=False, grad_wire=args.grad_wire)
-            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3,
-                                                                      capturable=use_graph,
-                                                                      fused=not args.no_fused_adam))
+            if args.flat_adam:  # libdmlb K5: parameters, moments and (in graph mode) gradients in flat buffers
+                from dmlcloud_b200.optim import FlatAdam
+
+                optimizer = FlatAdam(model.parameters(), lr=1e-3)
+            else:
+                optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph,
+                                             fused=not args.no_fused_adam)
+            self.pipeline.register_optimizer('adam', optimizer)
             self.loss = nn.CrossEntropyLoss()
             # whole-step CUDA graph after 3 eager steps (graphstep.py); at W > 1 it needs the peer communicator
             self.cuda_graph = use_graph and (world == 1 or self.pipeline.grad_syncs['cnn'].comm is not None)
@@ -306,7 +313,7 @@ def native_arm(args):
         'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP, bf16 autocast, Adam, 32 samples/rank/step, '
                                '5 metrics tracked + cross-rank metric exchange every step',
                    'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'grad_wire': args.grad_wire,
-                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last), 'adam': 'torch fused' if not args.no_fused_adam else 'torch foreach',
+                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last), 'adam': 'libdmlb FlatAdam (K5)' if args.flat_adam else ('torch fused' if not args.no_fused_adam else 'torch foreach'),
                    'graph_replays': stage._graph.replays if stage._graph is not None else 0,
                    'grad_route': sorted(set(sync.last_routes.values())),
                    'metric_route': 'peer' if pipeline.metric_comm is not None else ('single' if world == 1 else 'collective'),
@@ -418,6 +425,11 @@ def kernel_microbench(dev, peaks):
     sq = torch.zeros(1, dtype=torch.float64, device=dev)
     read_only = timed(lambda: N.check(lib.dmlb_bucket_sumsq_f32(src.data_ptr(), n, sq.data_ptr(), st)))
     write_only = timed(lambda: src.zero_())  # cudaMemset-class fill by torch: context for the write-heavy kernels
+    q = n // 4  # K5 on four quarter-size arrays carved out of `src` (all zero after the fill above: timing only)
+    adam_state = torch.zeros(2, dtype=torch.int64, device=dev)
+    quarters = [src.data_ptr() + 4 * q * i for i in range(4)]
+    adam = timed(lambda: N.check(lib.dmlb_adam_step_f32(quarters[0], quarters[1], quarters[2], quarters[3], q, 1e-3, 0.9,
+                                                        0.999, 1e-8, 0.0, 0, 0, None, 0.0, adam_state.data_ptr(), 1, st)))
     traffic = {'pack': ncu_traffic('pack_bf16_tma_kernel'), 'pack_regs': ncu_traffic('PackBf16'),
                'unpack_tma': ncu_traffic('unpack_bf16_tma_kernel'), 'unpack_regs': ncu_traffic('UnpackBf16'),
                'scale': ncu_traffic('ScaleInplace')}
@@ -435,7 +447,9 @@ def kernel_microbench(dev, peaks):
                           entry('dmlb_bucket_unpack_bf16_f32 (K2, default dispatch)', 6, n, unpack),
                           entry('dmlb_bucket_unpack_bf16_f32_tma (K2 via TMA bulk load + bulk store)', 6, n, unpack_tma),
                           entry('dmlb_bucket_unpack_bf16_f32_regs (K2 via registers)', 6, n, unpack_regs),
-                          entry('dmlb_bucket_scale_f32 (K1, fp32 wire, in place)', 8, n, scale)],
+                          entry('dmlb_bucket_scale_f32 (K1, fp32 wire, in place)', 8, n, scale),
+                          entry('dmlb_adam_step_f32 (K5, Adam step on a flat bucket: 16 B read + 12 B written per element)',
+                                28, q, adam)],
     }
     # ResNet-18 DDP buckets.  A single 10 us launch cannot be timed with an event pair (the pair itself
     # costs microseconds), so R x [L2 flush, kernel] is captured into a CUDA graph and timed against R x [L2 flush].

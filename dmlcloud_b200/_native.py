@@ -5,7 +5,8 @@ arithmetic raises.  `torch` is used by callers for device memory, streams and to
 """
 import ctypes
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64,
+                    c_void_p)
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libdmlb.so'
@@ -58,6 +59,8 @@ SIGNATURES = {
     'dmlb_bucket_round_bf16_f32': (c_int, [c_void_p, c_size_t, c_float, c_void_p, c_void_p]),
     'dmlb_bucket_sumsq_f32': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     'dmlb_bucket_clip_f32': (c_int, [c_void_p, c_size_t, c_void_p, c_float, c_void_p]),
+    'dmlb_adam_step_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_double, c_double, c_double,
+                                   c_double, c_double, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     'dmlb_multi_pack': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_float, c_void_p]),
     'dmlb_multi_unpack': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     'dmlb_ipc_get_handle': (c_int, [c_void_p, c_void_p]),

@@ -11,7 +11,8 @@ import sys
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-SOURCES = ['core.cu', 'bucket_kernels.cu', 'bucket_tma.cu', 'peer_comm.cu', 'metric_kernels.cu', 'shard_kernels.cu']
+SOURCES = ['core.cu', 'bucket_kernels.cu', 'bucket_tma.cu', 'peer_comm.cu', 'metric_kernels.cu', 'shard_kernels.cu',
+           'optim_kernels.cu']
 HEADERS = ['dmlb_common.cuh', 'peer_comm.cuh', '../../include/dmlb.h']
 LIB = HERE / 'libdmlb.so'
 STAMP = HERE / '.libdmlb.stamp'

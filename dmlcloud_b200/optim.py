@@ -1,0 +1,176 @@
+"""FlatAdam: Adam / AdamW whose whole step is ONE libdmlb launch over flat fp32 buffers.
+
+The reference calls `optimizer.step()` on whatever torch optimizer the user registered (stage.py:287-288; the examples
+use `torch.optim.Adam(lr=1e-3)`, examples/mnist.py:39).  `FlatAdam` is a drop-in for torch.optim.Adam / AdamW on fp32
+CUDA parameters:
+
+  * at construction every parameter of a group is moved into one flat fp32 buffer (`p.data` become views, 16-byte
+    aligned slots); `exp_avg` / `exp_avg_sq` are flat buffers of the same layout;
+  * `step()` is `dmlb_adam_step_f32` (csrc/optim_kernels.cu, 28 B/elem): one launch per group when the gradients are
+    views of one flat buffer with the same layout (what `graphstep.FlatGradBucket` sets up), else one launch per
+    parameter; the step count lives in device memory, so the optimizer is CUDA-graph capturable by construction;
+  * `step(clip=(sumsq, max_norm))` fuses `clip_grad_norm_` (stage.py:276-285): the coefficient is derived on the device
+    from a sum of squares that the gradient all-reduce already produced;
+  * `state_dict()` / `load_state_dict()` use torch.optim.Adam's format (per-parameter `step`, `exp_avg`, `exp_avg_sq`),
+    so checkpoints are interchangeable with the torch optimizer.
+
+Differences from torch.optim.Adam: no amsgrad, no sparse gradients, fp32 CUDA parameters only; the step count is kept
+per group, not per parameter (identical unless some parameters receive no gradient in some steps).
+"""
+import torch
+
+from . import _native as N
+
+SLOT = 4  # elements: every parameter starts on a 16-byte boundary of the flat buffers
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled_weight_decay=False,
+                 maximize=False):
+        if lr < 0.0 or eps < 0.0 or weight_decay < 0.0:
+            raise ValueError('lr, eps and weight_decay must be non-negative')
+        if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
+            raise ValueError(f'Invalid betas: {betas}')
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                        decoupled_weight_decay=decoupled_weight_decay, maximize=maximize,
+                        capturable=True,  # the step count is device-resident: always safe to capture
+                        # torch.optim.Adam's remaining group keys, so that a state_dict loads into the torch optimizer
+                        amsgrad=False, foreach=None, fused=None, differentiable=False)
+        super().__init__(params, defaults)
+        self._flat = [self._flatten(group) for group in self.param_groups]
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, '_flat'):  # groups added after construction get their own flat buffers
+            self._flat.append(self._flatten(self.param_groups[-1]))
+
+    # -- layout ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _flatten(group):
+        params = group['params']
+        if not params:
+            raise ValueError('FlatAdam: empty parameter group')
+        device = params[0].device
+        if device.type != 'cuda':
+            raise RuntimeError('FlatAdam runs on libdmlb CUDA kernels: parameters must live on a CUDA device '
+                               '(dmlcloud_b200 has no CPU fallback)')
+        N.cuda_lib(device.index)
+        offsets, total = [], 0
+        for p in params:
+            if p.dtype != torch.float32 or p.device != device or p.is_sparse:
+                raise RuntimeError('FlatAdam expects dense fp32 parameters on one CUDA device')
+            offsets.append(total)
+            total += -(-p.numel() // SLOT) * SLOT
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, off in zip(params, offsets):
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        return {
+            'device': device, 'offsets': offsets, 'total': total, 'param': flat,
+            'exp_avg': torch.zeros_like(flat), 'exp_avg_sq': torch.zeros_like(flat),
+            'state': torch.zeros(2, dtype=torch.int64, device=device),  # dmlb_adam_state {step, done|pad}
+        }
+
+    def _attached(self, group, flat):
+        """True while every parameter still is the view of the flat buffer it was given at construction."""
+        base = flat['param'].data_ptr()
+        return all(p.data_ptr() == base + 4 * off for p, off in zip(group['params'], flat['offsets']))
+
+    @staticmethod
+    def _flat_grad_base(group, flat):
+        """Address of a flat gradient buffer with this group's layout, or None."""
+        g0 = group['params'][0].grad
+        if g0 is None:
+            return None
+        base = g0.data_ptr()
+        for p, off in zip(group['params'], flat['offsets']):
+            g = p.grad
+            if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != base + 4 * off:
+                return None
+        return base
+
+    # -- step --------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, closure=None, clip=None):
+        """clip: None or (sumsq, max_norm) with `sumsq` a 1-element fp64 CUDA tensor holding sum(grad^2) over exactly the
+        gradients this optimizer owns — the gradients are scaled by min(1, max_norm / (sqrt(sumsq) + 1e-6)) on the fly."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group, flat in zip(self.param_groups, self._flat):
+            if not self._attached(group, flat):
+                raise RuntimeError('FlatAdam: a parameter no longer aliases the flat buffer (its .data was replaced)')
+            lib = N.cuda_lib(flat['device'].index)
+            beta1, beta2 = group['betas']
+            sumsq_ptr, max_norm = (clip[0].data_ptr(), float(clip[1])) if clip is not None else (None, 0.0)
+            common = (float(group['lr']), float(beta1), float(beta2), float(group['eps']), float(group['weight_decay']),
+                      int(group['decoupled_weight_decay']), int(group['maximize']), sumsq_ptr, max_norm,
+                      flat['state'].data_ptr())
+            st = N.stream_ptr()
+            base = self._flat_grad_base(group, flat)
+            if base is not None:  # one launch for the whole group
+                N.check(lib.dmlb_adam_step_f32(flat['param'].data_ptr(), base, flat['exp_avg'].data_ptr(),
+                                               flat['exp_avg_sq'].data_ptr(), flat['total'], *common, 1, st), 'adam_step')
+                continue
+            live = [(p, off) for p, off in zip(group['params'], flat['offsets']) if p.grad is not None]
+            for i, (p, off) in enumerate(live):
+                g = p.grad
+                if g.is_sparse or g.dtype != torch.float32:
+                    raise RuntimeError('FlatAdam expects dense fp32 gradients')
+                g = g.contiguous()
+                N.check(lib.dmlb_adam_step_f32(flat['param'].data_ptr() + 4 * off, g.data_ptr(),
+                                               flat['exp_avg'].data_ptr() + 4 * off,
+                                               flat['exp_avg_sq'].data_ptr() + 4 * off, p.numel(), *common,
+                                               int(i == len(live) - 1), st), 'adam_step')
+        return loss
+
+    def steps_taken(self, group=0):
+        """Host copy of the device-resident step count (synchronises)."""
+        return int(self._flat[group]['state'][0].item())
+
+    # -- checkpoint: torch.optim.Adam's format -----------------------------------------------------------------------
+    def state_dict(self):
+        state, groups, index = {}, [], 0
+        for group, flat in zip(self.param_groups, self._flat):
+            step = flat['state'][0].to(torch.float32).cpu()
+            ids = []
+            for p, off in zip(group['params'], flat['offsets']):
+                n = p.numel()
+                if int(step) > 0:
+                    state[index] = {'step': step.clone(),
+                                    'exp_avg': flat['exp_avg'][off:off + n].view(p.shape).clone(),
+                                    'exp_avg_sq': flat['exp_avg_sq'][off:off + n].view(p.shape).clone()}
+                ids.append(index)
+                index += 1
+            packed = {k: v for k, v in group.items() if k != 'params'}
+            packed['params'] = ids
+            groups.append(packed)
+        return {'state': state, 'param_groups': groups}
+
+    def load_state_dict(self, state_dict):
+        groups = state_dict['param_groups']
+        if len(groups) != len(self.param_groups) or any(len(a['params']) != len(b['params'])
+                                                        for a, b in zip(groups, self.param_groups)):
+            raise ValueError('loaded state dict has a different number of parameter groups / parameters')
+        for saved, group, flat in zip(groups, self.param_groups, self._flat):
+            for key, value in saved.items():
+                if key not in ('params', 'capturable', 'fused', 'foreach', 'differentiable', 'amsgrad'):
+                    group[key] = value
+            flat['exp_avg'].zero_()
+            flat['exp_avg_sq'].zero_()
+            steps = set()
+            for idx, p, off in zip(saved['params'], group['params'], flat['offsets']):
+                entry = state_dict['state'].get(idx)
+                if entry is None:
+                    continue
+                n = p.numel()
+                flat['exp_avg'][off:off + n].copy_(entry['exp_avg'].reshape(-1))
+                flat['exp_avg_sq'][off:off + n].copy_(entry['exp_avg_sq'].reshape(-1))
+                steps.add(int(entry['step']))
+            if len(steps) > 1:
+                raise ValueError(f'FlatAdam keeps one step count per group; the loaded state has {sorted(steps)}')
+            flat['state'].zero_()
+            flat['state'][0] = steps.pop() if steps else 0

@@ -105,6 +105,27 @@ int dmlb_bucket_sumsq_f32(const float *buf, size_t n, double *sumsq, void *strea
 /* buf *= min(1, max_norm / (sqrt(*sumsq) + 1e-6))  — second half of clip_grad_norm_; reads *sumsq on device, no host sync */
 int dmlb_bucket_clip_f32(float *buf, size_t n, const double *sumsq, float max_norm, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* K5: optimizer step on a flat fp32 bucket                                                            */
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Replaces `optimizer.step()` (reference stage.py:287-288; torch.optim.Adam / AdamW as registered by the user,
+ * examples/mnist.py:39) for parameters, gradients and moments that live in flat fp32 buffers: one elementwise pass,
+ * 28 B/elem.  t = state->step + 1;  g = coef * grad (coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6)) when `sumsq` is
+ * given — clip_grad_norm_ of stage.py:276-285 fused in — else 1; negated for `maximize`);  L2 decay g += wd * p, or
+ * decoupled (AdamW) p *= 1 - lr * wd;  m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g^2;
+ * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps).  `state` is a 16-byte zero-initialised DEVICE
+ * block holding the step count (CUDA-graph replays advance it); with advance == 0 the launch leaves it untouched, so a
+ * step made of several launches (one per parameter) advances it with the last one only.  Hyper-parameters are doubles
+ * (python floats): derived scalars such as 1 - beta2 are formed in fp64 and rounded once, as torch does. */
+typedef struct {
+    int64_t step;
+    uint32_t done; /* internal: CTAs that have finished the current launch */
+    uint32_t _pad;
+} dmlb_adam_state;
+int dmlb_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n, double lr,
+                       double beta1, double beta2, double eps, double weight_decay, int decoupled, int maximize,
+                       const double *sumsq, float max_norm, dmlb_adam_state *state, int advance, void *stream);
+
 /* Multi-tensor variants: gather `count` parameter gradients straight into / out of one flat wire buffer (the graph-
  * captured step keeps no DDP Reducer).  `segs` is a DEVICE array of dmlb_seg built once at registration. */
 typedef struct {

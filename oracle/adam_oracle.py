@@ -1,0 +1,46 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+numpy restatement of the optimizer step the reference runs at stage.py:287-288 (`optimizer.step()` for every registered
+optimizer; the examples register `torch.optim.Adam(lr=1e-3)`, examples/mnist.py:39).  The arithmetic lives in torch
+(third-party, unpinned in requirements.txt:1; this image: 2.11.0+cu128): torch/optim/adam.py `_single_tensor_adam`
+(lines 347ff: weight decay 69-82, moments 110-129, bias corrections 184-189, update 198-200), and
+torch/nn/utils/clip_grad.py for the optional clip coefficient (stage.py:276-285).
+
+    t += 1
+    g  = coef * grad                     (coef = min(1, max_norm / (||grad||_2 + 1e-6)) when clipping, else 1; -coef: maximize)
+    L2 decay:  g += wd * p               decoupled (AdamW):  p *= 1 - lr * wd
+    m  = lerp(m, g, 1 - beta1)           v = beta2 * v + (1 - beta2) * g * g
+    p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+
+Pinned by tests/test_oracle_pins.py against torch.optim.Adam / AdamW themselves (fp64: 1e-12; fp32: a few ulp).
+"""
+import numpy as np
+
+
+def clip_coef(sumsq, max_norm):
+    """torch.nn.utils.clip_grad_norm_: fp32 arithmetic on the total norm."""
+    total = np.float32(np.sqrt(np.float64(sumsq)))
+    c = np.float32(max_norm) / (total + np.float32(1e-6))
+    return np.float32(min(c, np.float32(1.0)))
+
+
+def adam_step(p, g, m, v, t, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, maximize=False,
+              coef=1.0, dtype=np.float64):
+    """One step.  `t` is the step count AFTER this step (1 for the first).  Returns new (p, m, v) in `dtype`.
+    dtype=np.float32 rounds after every operation like an fp32 kernel without fused multiply-adds."""
+    f = dtype
+    p, g, m, v = (np.asarray(x, dtype=f).copy() for x in (p, g, m, v))
+    b1, b2 = f(betas[0]), f(betas[1])
+    g = g * f(-coef if maximize else coef)
+    if weight_decay != 0:
+        if decoupled:
+            p = p * f(1.0 - lr * weight_decay)
+        else:
+            g = g + f(weight_decay) * p
+    w = f(1.0 - betas[0])  # python-float expressions first, one rounding to the working dtype (as torch passes scalars)
+    m = m + w * (g - m) if w < 0.5 else g - (g - m) * (f(1) - w)
+    v = b2 * v + f(1.0 - betas[1]) * g * g
+    step_size = f(np.float64(lr) / (1.0 - np.float64(betas[0]) ** t))
+    bc2_sqrt = f(np.sqrt(1.0 - np.float64(betas[1]) ** t))
+    p = p - step_size * m / (np.sqrt(v) / bc2_sqrt + f(eps))
+    return p, m, v

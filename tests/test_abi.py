@@ -87,3 +87,7 @@ def test_product_refuses_to_compute_without_cuda():
 
     with pytest.raises(RuntimeError):
         GradBucketSync('cpu')
+    from dmlcloud_b200.optim import FlatAdam
+
+    with pytest.raises(RuntimeError, match='CUDA'):
+        FlatAdam([torch.nn.Parameter(torch.zeros(3))])

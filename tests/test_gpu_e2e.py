@@ -33,7 +33,7 @@ def batches(seed, steps, batch):
             for _ in range(steps)]
 
 
-def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0, graph=False):
+def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0, graph=False, flat_adam=False):
     from dmlcloud_b200 import TrainValStage
     from dmlcloud_b200.pipeline import TrainingPipeline
 
@@ -46,7 +46,13 @@ def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0
             self.pipeline.register_dataset('val', batches(200 + rank, meta['val_steps'], meta['batch']), verbose=False)
             model = make_cnn()
             self.pipeline.register_model('cnn', model, verbose=False)
-            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph))
+            if flat_adam:  # libdmlb K5 instead of the torch optimizer the reference run used
+                from dmlcloud_b200.optim import FlatAdam
+
+                optimizer = FlatAdam(model.parameters(), lr=1e-3)
+            else:
+                optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph)
+            self.pipeline.register_optimizer('adam', optimizer)
             self.loss = torch.nn.CrossEntropyLoss()
             self.live_metrics_every = live_every
             self.cuda_graph = graph
@@ -120,6 +126,29 @@ def test_train_w1_cuda_graph_step_matches_reference_run():
         compare(p, stage, psum, pabs, gold['ranks'][0])
         assert stage._graph is not None and stage._graph.replays == gold['meta']['train_steps'] * gold['meta']['epochs'] - 3
         assert stage._graph.bucket.attached()
+    finally:
+        deinitialize_torch_distributed()
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_train_w1_flat_adam_matches_reference_run(graph):
+    """Same golden run with `optimizer.step()` on libdmlb (FlatAdam, K5): per-parameter launches in the eager loop, one
+    launch on the flat buffers inside the captured step."""
+    from dmlcloud_b200 import _native as N
+    from dmlcloud_b200.util.distributed import deinitialize_torch_distributed, init_process_group_dummy
+
+    gold = load_json('train_w1.json')
+    steps = gold['meta']['train_steps'] * gold['meta']['epochs']
+    init_process_group_dummy()
+    try:
+        before = N.launch_count()
+        p, stage, psum, pabs = run_product(0, gold['meta'], graph=graph, flat_adam=True)
+        compare(p, stage, psum, pabs, gold['ranks'][0])
+        assert p.optimizers['adam'].steps_taken() == steps
+        if graph:
+            assert stage._graph is not None and stage._graph.replays == steps - 3 and stage._graph.bucket.attached()
+        else:
+            assert N.launch_count() - before >= 6 * steps  # six parameter tensors, one K5 launch each per step
     finally:
         deinitialize_torch_distributed()
 
