@@ -50,14 +50,21 @@ def parse_args():
     ap.add_argument('--grad-route', choices=['auto', 'peer', 'nccl'], default='auto')
     ap.add_argument('--metric-route', choices=['auto', 'peer', 'collective'], default='auto')
     ap.add_argument('--no-graph', action='store_true', help='eager step loop instead of the whole-step CUDA graph')
-    ap.add_argument('--no-fused-adam', action='store_true', help='torch.optim.Adam(fused=False)')
-    ap.add_argument('--flat-adam', action='store_true',
-                    help='dmlcloud_b200.optim.FlatAdam (libdmlb K5: one launch over flat buffers) instead of torch.optim.Adam')
+    ap.add_argument('--adam', choices=['flat', 'torch-fused', 'torch-foreach'], default='flat',
+                    help='optimizer of the step: dmlcloud_b200.optim.FlatAdam (libdmlb K5, one launch over flat buffers; '
+                         'default, +7%% over torch-fused in the graph step, profiles/README.md) or torch.optim.Adam')
+    ap.add_argument('--no-fused-adam', action='store_true', help='same as --adam torch-foreach')
+    ap.add_argument('--flat-adam', action='store_true', help='same as --adam flat (the default)')
     ap.add_argument('--channels-last', action='store_true', help='keep model + images in NHWC (cuDNN bf16 native layout)')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=3000)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.no_fused_adam:
+        args.adam = 'torch-foreach'
+    if args.flat_adam:
+        args.adam = 'flat'
+    return args
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -185,13 +192,13 @@ def native_arm(args):
             if args.channels_last:
                 model = model.to(memory_format=torch.channels_last)
             self.pipeline.register_model('cnn', model, verbose=False, grad_wire=args.grad_wire)
-            if args.flat_adam:  # libdmlb K5: parameters, moments and (in graph mode) gradients in flat buffers
+            if args.adam == 'flat':  # libdmlb K5: parameters, moments and (in graph mode) gradients in flat buffers
                 from dmlcloud_b200.optim import FlatAdam
 
                 optimizer = FlatAdam(model.parameters(), lr=1e-3)
             else:
                 optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=use_graph,
-                                             fused=not args.no_fused_adam)
+                                             fused=args.adam == 'torch-fused')
             self.pipeline.register_optimizer('adam', optimizer)
             self.loss = nn.CrossEntropyLoss()
             # whole-step CUDA graph after 3 eager steps (graphstep.py); at W > 1 it needs the peer communicator
@@ -313,7 +320,7 @@ def native_arm(args):
         'config': {'workload': 'MNIST CNN (examples/mnist.py:27-36) DDP, bf16 autocast, Adam, 32 samples/rank/step, '
                                '5 metrics tracked + cross-rank metric exchange every step',
                    'global_batch': BATCH * world, 'parallelism': f'dp{world}', 'grad_wire': args.grad_wire,
-                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last), 'adam': 'libdmlb FlatAdam (K5)' if args.flat_adam else ('torch fused' if not args.no_fused_adam else 'torch foreach'),
+                   'cuda_graph': bool(stage._graph is not None), 'channels_last': bool(args.channels_last), 'adam': {'flat': 'libdmlb FlatAdam (K5)', 'torch-fused': 'torch fused', 'torch-foreach': 'torch foreach'}[args.adam],
                    'graph_replays': stage._graph.replays if stage._graph is not None else 0,
                    'grad_route': sorted(set(sync.last_routes.values())),
                    'metric_route': 'peer' if pipeline.metric_comm is not None else ('single' if world == 1 else 'collective'),
