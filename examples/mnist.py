@@ -1,6 +1,6 @@
 """MNIST CNN with dmlcloud_b200 — the reference's examples/mnist.py, line for line where the API is the same, with the
-B200 extras switched on: device-resident sharded dataset, bf16 gradient wire, whole-step CUDA graph, per-step metric
-exchange.  No network here, so the images are synthetic uint8 (same shape and dtype as MNIST).
+B200 extras switched on: device-resident sharded dataset, bf16 gradient wire, whole-step CUDA graph, Adam as one
+launch on flat buffers, per-step metric exchange.  No network here, so the images are synthetic uint8 (same shape and dtype as MNIST).
 
     python examples/mnist.py                                        # one GPU
     torchrun --standalone --local-addr 127.0.0.1 --nproc-per-node 8 examples/mnist.py
@@ -13,6 +13,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from torch import nn
 
+from dmlcloud_b200.optim import FlatAdam
 from dmlcloud_b200.pipeline import TrainingPipeline
 from dmlcloud_b200.stage import TrainValStage
 from dmlcloud_b200.util.data import DeviceShardedDataset
@@ -42,7 +43,9 @@ class MNISTStage(TrainValStage):
             nn.Flatten(), nn.Linear(784, 10),
         )
         self.pipeline.register_model('cnn', model, grad_wire='bf16')
-        self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True))
+        # the reference registers torch.optim.Adam(model.parameters(), lr=1e-3); that still works here (pass
+        # capturable=True for the captured step).  FlatAdam is the same optimizer as ONE libdmlb launch per step.
+        self.pipeline.register_optimizer('adam', FlatAdam(model.parameters(), lr=1e-3))
         self.loss = nn.CrossEntropyLoss()
         self.cuda_graph = True          # capture the whole step after 3 eager steps
         self.live_metrics_every = 50    # running metrics cross the ranks every 50 steps (one fused kernel)
