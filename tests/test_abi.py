@@ -68,6 +68,15 @@ def test_argument_validation_needs_no_gpu():
     arenas = (ctypes.c_void_p * 1)(None)
     assert lib.dmlb_comm_create(ctypes.byref(comm), 9, 0, arenas, 1024) == N.EINVAL
     assert lib.dmlb_comm_create(ctypes.byref(comm), 1, 0, arenas, 1024) == N.EALIGN
+    # K5: 17 arguments (doubles for the hyper-parameters) marshalled through ctypes; rejected before any CUDA call
+    a = ctypes.c_void_p(256)
+    adam = lambda p, state, beta1, n=16: lib.dmlb_adam_step_f32(p, a, a, a, n, 1e-3, beta1, 0.999, 1e-8, 0.0, 0, 0, None,  # noqa: E731
+                                                                0.0, state, 1, None)
+    assert adam(a, None, 0.9) == N.EINVAL          # no state block
+    assert adam(None, a, 0.9) == N.EINVAL          # no parameters
+    assert adam(a, a, 1.0) == N.EINVAL             # beta1 outside [0, 1)
+    assert adam(ctypes.c_void_p(258), a, 0.9) == N.EALIGN
+    assert adam(a, ctypes.c_void_p(260), 0.9) == N.EALIGN  # the state block holds an int64
 
 
 def test_product_refuses_to_compute_without_cuda():
