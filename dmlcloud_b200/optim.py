@@ -26,7 +26,10 @@ SLOT = 4  # elements: every parameter starts on a 16-byte boundary of the flat b
 
 class FlatAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled_weight_decay=False,
-                 maximize=False):
+                 maximize=False, _lib=None):
+        # _lib: test hook (tests/test_host_logic.py injects oracle/adam_oracle.py behind the C signature to exercise the
+        # layout / checkpoint logic on a CPU-only box); the product always runs libdmlb on a CUDA device.
+        self._lib_override = _lib
         if lr < 0.0 or eps < 0.0 or weight_decay < 0.0:
             raise ValueError('lr, eps and weight_decay must be non-negative')
         if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
@@ -45,16 +48,18 @@ class FlatAdam(torch.optim.Optimizer):
             self._flat.append(self._flatten(self.param_groups[-1]))
 
     # -- layout ------------------------------------------------------------------------------------------------------
-    @staticmethod
-    def _flatten(group):
+    def _lib(self, device):
+        return self._lib_override if self._lib_override is not None else N.cuda_lib(device.index)
+
+    def _flatten(self, group):
         params = group['params']
         if not params:
             raise ValueError('FlatAdam: empty parameter group')
         device = params[0].device
-        if device.type != 'cuda':
+        if device.type != 'cuda' and self._lib_override is None:
             raise RuntimeError('FlatAdam runs on libdmlb CUDA kernels: parameters must live on a CUDA device '
                                '(dmlcloud_b200 has no CPU fallback)')
-        N.cuda_lib(device.index)
+        self._lib(device)
         offsets, total = [], 0
         for p in params:
             if p.dtype != torch.float32 or p.device != device or p.is_sparse:
@@ -103,13 +108,13 @@ class FlatAdam(torch.optim.Optimizer):
         for group, flat in zip(self.param_groups, self._flat):
             if not self._attached(group, flat):
                 raise RuntimeError('FlatAdam: a parameter no longer aliases the flat buffer (its .data was replaced)')
-            lib = N.cuda_lib(flat['device'].index)
+            lib = self._lib(flat['device'])
             beta1, beta2 = group['betas']
             sumsq_ptr, max_norm = (clip[0].data_ptr(), float(clip[1])) if clip is not None else (None, 0.0)
             common = (float(group['lr']), float(beta1), float(beta2), float(group['eps']), float(group['weight_decay']),
                       int(group['decoupled_weight_decay']), int(group['maximize']), sumsq_ptr, max_norm,
                       flat['state'].data_ptr())
-            st = N.stream_ptr()
+            st = N.stream_ptr() if self._lib_override is None else None
             base = self._flat_grad_base(group, flat)
             if base is not None:  # one launch for the whole group
                 N.check(lib.dmlb_adam_step_f32(flat['param'].data_ptr(), base, flat['exp_avg'].data_ptr(),

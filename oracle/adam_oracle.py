@@ -44,3 +44,34 @@ def adam_step(p, g, m, v, t, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay
     bc2_sqrt = f(np.sqrt(1.0 - np.float64(betas[1]) ** t))
     p = p - step_size * m / (np.sqrt(v) / bc2_sqrt + f(eps))
     return p, m, v
+
+
+class OracleAdamLib:
+    """Stands in for libdmlb behind `dmlb_adam_step_f32`'s C signature on HOST memory (tests inject it through
+    FlatAdam(_lib=...) to run the optimizer's layout / checkpoint logic on a CPU-only box).  fp32 arithmetic."""
+
+    def __init__(self):
+        self.launches = 0
+
+    @staticmethod
+    def _view(ptr, n, ctype):
+        import ctypes
+
+        return np.ctypeslib.as_array((ctype * n).from_address(ptr))
+
+    def dmlb_adam_step_f32(self, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled,
+                           maximize, sumsq, max_norm, state, advance, stream):
+        import ctypes
+
+        self.launches += 1
+        p, g, m, v = (self._view(x, n, ctypes.c_float) for x in (param, grad, exp_avg, exp_avg_sq))
+        st = self._view(state, 2, ctypes.c_int64)
+        coef = 1.0
+        if sumsq:
+            coef = float(clip_coef(self._view(sumsq, 1, ctypes.c_double)[0], max_norm))
+        p2, m2, v2 = adam_step(p, g, m, v, int(st[0]) + 1, lr=lr, betas=(beta1, beta2), eps=eps, weight_decay=weight_decay,
+                               decoupled=bool(decoupled), maximize=bool(maximize), coef=coef, dtype=np.float32)
+        p[:], m[:], v[:] = p2, m2, v2
+        if advance:
+            st[0] += 1
+        return 0

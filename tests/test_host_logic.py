@@ -240,6 +240,136 @@ class TestTrackerHostLogic:
 
 
 # -------------------------------------------------------------------------------------------------------------- shards
+class TestFlatAdamHostLogic:
+    """dmlcloud_b200.optim.FlatAdam's host side — flat layout, one-launch vs per-parameter dispatch, torch-compatible
+    checkpoints, parameter groups — on a CPU-only box: oracle/adam_oracle.OracleAdamLib is injected behind the C
+    signature (FlatAdam(_lib=...)); the kernel itself is checked on the GPU (tests/test_gpu_optim.py).  The reference
+    for every comparison is the optimizer the reference steps: torch.optim.Adam / AdamW (stage.py:287-288)."""
+
+    @staticmethod
+    def _model(seed):
+        torch.manual_seed(seed)
+        return torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+
+    @staticmethod
+    def _grads(model, step):
+        g = torch.Generator().manual_seed(100 + step)
+        return [torch.randn(p.shape, generator=g) * (0.01 if step % 2 else 1.0) for p in model.parameters()]
+
+    @pytest.mark.parametrize('decoupled', [False, True])
+    @pytest.mark.parametrize('flat_grads', [False, True])
+    def test_step_paths_match_torch(self, decoupled, flat_grads):
+        from dmlcloud_b200.graphstep import FlatGradBucket
+        from dmlcloud_b200.optim import FlatAdam
+        from oracle.adam_oracle import OracleAdamLib
+
+        lib = OracleAdamLib()
+        a, b = self._model(0), self._model(0)
+        ref = (torch.optim.AdamW if decoupled else torch.optim.Adam)(a.parameters(), lr=2e-3, weight_decay=0.02)
+        opt = FlatAdam(b.parameters(), lr=2e-3, weight_decay=0.02, decoupled_weight_decay=decoupled, _lib=lib)
+        assert all(torch.equal(x, y) for x, y in zip(a.parameters(), b.parameters()))  # flattening keeps the values
+        flat = opt._flat[0]['param']
+        assert all(p.data_ptr() == flat.data_ptr() + 4 * off for p, off in zip(b.parameters(), opt._flat[0]['offsets']))
+        assert all(off % 4 == 0 for off in opt._flat[0]['offsets'])  # 16-byte slots
+        bucket = FlatGradBucket(list(b.parameters()), 'cpu') if flat_grads else None
+        for step in range(8):
+            for p, q, g in zip(a.parameters(), b.parameters(), self._grads(a, step)):
+                p.grad = g.clone()
+                if flat_grads:
+                    q.grad.copy_(g)
+                else:
+                    q.grad = g.clone()
+            before = lib.launches
+            ref.step()
+            opt.step()
+            assert lib.launches - before == (1 if flat_grads else 4)
+        assert opt.steps_taken() == 8 and (bucket is None or bucket.attached())
+        for p, q in zip(a.parameters(), b.parameters()):
+            torch.testing.assert_close(q, p, rtol=1e-5, atol=1e-6)
+        x = torch.randn(4, 7)
+        torch.testing.assert_close(b(x), a(x), rtol=1e-4, atol=1e-5)  # the model computes with the flat views
+
+    def test_checkpoints_are_interchangeable_with_torch_adam(self):
+        from dmlcloud_b200.optim import FlatAdam
+        from oracle.adam_oracle import OracleAdamLib
+
+        a, b = self._model(1), self._model(1)
+        ref = torch.optim.Adam(a.parameters(), lr=1e-3)
+        opt = FlatAdam(b.parameters(), lr=1e-3, _lib=OracleAdamLib())
+        assert opt.state_dict()['state'] == {}
+        assert set(opt.state_dict()['param_groups'][0]) == set(ref.state_dict()['param_groups'][0])
+        for step in range(3):
+            for p, g in zip(a.parameters(), self._grads(a, step)):
+                p.grad = g
+            ref.step()
+        with torch.no_grad():
+            for p, q in zip(a.parameters(), b.parameters()):
+                q.copy_(p)
+        opt.load_state_dict(ref.state_dict())  # torch -> FlatAdam
+        assert opt.steps_taken() == 3
+        for step in range(3, 6):
+            for p, q, g in zip(a.parameters(), b.parameters(), self._grads(a, step)):
+                p.grad, q.grad = g.clone(), g.clone()
+            ref.step()
+            opt.step()
+        for p, q in zip(a.parameters(), b.parameters()):
+            torch.testing.assert_close(q, p, rtol=1e-5, atol=1e-6)
+        c = self._model(1)
+        with torch.no_grad():
+            for q, r in zip(b.parameters(), c.parameters()):
+                r.copy_(q)
+        ref2 = torch.optim.Adam(c.parameters(), lr=1e-3)
+        saved = opt.state_dict()
+        for group in saved['param_groups']:
+            group['capturable'] = False  # the plain torch optimizer keeps `step` on the host
+        ref2.load_state_dict(saved)  # FlatAdam -> torch
+        for step in range(6, 8):
+            for q, r, g in zip(b.parameters(), c.parameters(), self._grads(a, step)):
+                q.grad, r.grad = g.clone(), g.clone()
+            opt.step()
+            ref2.step()
+        for q, r in zip(b.parameters(), c.parameters()):
+            torch.testing.assert_close(q, r, rtol=1e-5, atol=1e-6)
+        bad = ref.state_dict()
+        bad['state'][0]['step'] = torch.tensor(7.0)
+        with pytest.raises(ValueError, match='one step count per group'):
+            opt.load_state_dict(bad)
+
+    def test_groups_clip_and_detached_parameters(self):
+        from dmlcloud_b200.optim import FlatAdam
+        from oracle import adam_oracle
+
+        lib = adam_oracle.OracleAdamLib()
+        a = self._model(2)
+        before = [p.detach().clone() for p in a.parameters()]
+        opt = FlatAdam(a.parameters(), lr=1e-3, _lib=lib)
+        grads = self._grads(a, 0)
+        for p, g in zip(a.parameters(), grads):
+            p.grad = g.clone()
+        sumsq = torch.tensor([sum(float((g.double() ** 2).sum()) for g in grads)], dtype=torch.float64)
+        opt.step(clip=(sumsq, 0.5))  # clip_grad_norm_ fused into the step
+        ref = [torch.nn.Parameter(x.clone()) for x in before]
+        for r, g in zip(ref, grads):
+            r.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 0.5)
+        torch.optim.Adam(ref, lr=1e-3).step()
+        for p, r in zip(a.parameters(), ref):
+            torch.testing.assert_close(p, r, rtol=1e-5, atol=1e-6)
+        extra = torch.nn.Parameter(torch.randn(6))
+        opt.add_param_group({'params': [extra], 'lr': 1e-2})  # a second group gets its own flat buffers and step count
+        extra.grad = torch.randn(6)
+        opt.zero_grad()
+        assert all(p.grad is None for p in a.parameters()) and extra.grad is None
+        extra.grad = torch.randn(6)
+        opt.step()  # group 0 has no gradients: nothing to do there, its step count stays
+        assert opt.steps_taken(0) == 1 and opt.steps_taken(1) == 1
+        next(a.parameters()).data = torch.zeros_like(next(a.parameters()))  # someone replaced a parameter's storage
+        with pytest.raises(RuntimeError, match='no longer aliases'):
+            opt.step()
+        with pytest.raises(ValueError):
+            FlatAdam([torch.nn.Parameter(torch.zeros(2))], betas=(1.0, 0.9), _lib=lib)
+
+
 class TestShardingHost:
     def test_reference_golden_lists(self):
         from dmlcloud_b200.util.data import shard_indices
