@@ -49,3 +49,34 @@ def _undefined(path):
 @pytest.mark.parametrize('path', FILES, ids=lambda p: str(p.relative_to(ROOT)))
 def test_no_undefined_global_names(path):
     assert _undefined(path) == []
+
+
+def _dmlb_calls(path):
+    import ast
+
+    tree = ast.parse(path.read_text(), str(path))
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith('dmlb_'):
+            yield node
+
+
+@pytest.mark.parametrize('path', FILES, ids=lambda p: str(p.relative_to(ROOT)))
+def test_c_abi_calls_pass_the_declared_number_of_arguments(path):
+    """ctypes only complains about a wrong argument count when the call executes — on a GPU box for most call sites.
+    Every `<lib>.dmlb_xxx(...)` call in the tree is checked against dmlcloud_b200/_native.py SIGNATURES here."""
+    import ast
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    from dmlcloud_b200 import _native as N
+
+    for call in _dmlb_calls(path):
+        name = call.func.attr
+        assert name in N.SIGNATURES, f'{path.name}:{call.lineno}: {name} is not declared'
+        assert not call.keywords, f'{path.name}:{call.lineno}: keyword arguments in a C call'
+        want = len(N.SIGNATURES[name][1])
+        fixed = [a for a in call.args if not isinstance(a, ast.Starred)]
+        if len(fixed) == len(call.args):
+            assert len(call.args) == want, f'{path.name}:{call.lineno}: {name} takes {want} arguments, {len(call.args)} given'
+        else:  # a *tuple in the call: at least the explicit ones must fit
+            assert len(fixed) < want, f'{path.name}:{call.lineno}: {name} takes {want} arguments'
