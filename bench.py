@@ -436,7 +436,8 @@ def kernel_microbench(dev, peaks):
     adam_state = torch.zeros(2, dtype=torch.int64, device=dev)
     quarters = [src.data_ptr() + 4 * q * i for i in range(4)]
     adam = timed(lambda: N.check(lib.dmlb_adam_step_f32(quarters[0], quarters[1], quarters[2], quarters[3], q, 1e-3, 0.9,
-                                                        0.999, 1e-8, 0.0, 0, 0, None, 0.0, adam_state.data_ptr(), 1, st)))
+                                                        0.999, 1e-8, 0.0, 0, 0, None, 0.0, adam_state.data_ptr(), 1, None,
+                                                        st)))
     traffic = {'pack': ncu_traffic('pack_bf16_tma_kernel'), 'pack_regs': ncu_traffic('PackBf16'),
                'unpack_tma': ncu_traffic('unpack_bf16_tma_kernel'), 'unpack_regs': ncu_traffic('UnpackBf16'),
                'scale': ncu_traffic('ScaleInplace')}

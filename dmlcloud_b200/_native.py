@@ -16,7 +16,11 @@ EINVAL, EALIGN, ECAPACITY, ESTATE = -10001, -10002, -10003, -10004
 WIRE_F32, WIRE_BF16 = 0, 1
 F32, F64, F16, BF16, I64, I32, U8 = range(7)
 MEAN, SUM, MIN, MAX = range(4)
-METRIC_OK, METRIC_SPLIT_VOTE, METRIC_LAYOUT = 0, 1, 2
+METRIC_OK, METRIC_SPLIT_VOTE, METRIC_LAYOUT, METRIC_TIMEOUT = 0, 1, 2, 3
+SRC_FEED = 7
+FEED_WIDTH = 16
+STEP_METRIC_MAX_CELLS = 1023
+ABI_VERSION = 2
 IPC_HANDLE_BYTES = 64
 MAX_WORLD = 8
 MAX_FOLD_ENTRIES = 32
@@ -35,6 +39,15 @@ class FoldEntry(Structure):
 
 class Range(Structure):
     _fields_ = [('begin', c_int32), ('end', c_int32)]
+
+
+class StepMetrics(Structure):
+    """dmlb_step_metrics: descriptor of the per-step metric exchange fused into the gradient all-reduce."""
+    _fields_ = [('acc', c_void_p), ('cnt', c_void_p), ('desc', c_void_p), ('counter', c_void_p), ('out_ring', c_void_p),
+                ('feed', c_void_p), ('layout_hash', c_uint64), ('n_cells', c_int32), ('capacity', c_int32),
+                ('ring_slots', c_int32), ('feed_slots', c_int32), ('n_folds', c_int32), ('n_ranges', c_int32),
+                ('n_global_ranges', c_int32), ('_pad', c_int32), ('folds', FoldEntry * MAX_FOLD_ENTRIES),
+                ('ranges', Range * MAX_RANGES)]
 
 
 # name -> (restype, argtypes); must list every symbol include/dmlb.h declares (tests/test_abi.py checks both ways)
@@ -60,7 +73,10 @@ SIGNATURES = {
     'dmlb_bucket_sumsq_f32': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     'dmlb_bucket_clip_f32': (c_int, [c_void_p, c_size_t, c_void_p, c_float, c_void_p]),
     'dmlb_adam_step_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_double, c_double, c_double,
-                                   c_double, c_double, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p]),
+                                   c_double, c_double, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                                   c_void_p]),
+    'dmlb_sgd_step_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_double, c_double, c_double, c_double, c_int,
+                                  c_int, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p]),
     'dmlb_multi_pack': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_float, c_void_p]),
     'dmlb_multi_unpack': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     'dmlb_ipc_get_handle': (c_int, [c_void_p, c_void_p]),
@@ -69,12 +85,24 @@ SIGNATURES = {
     'dmlb_comm_arena_bytes': (c_size_t, [c_size_t]),
     'dmlb_comm_create': (c_int, [POINTER(c_void_p), c_int, c_int, POINTER(c_void_p), c_size_t]),
     'dmlb_comm_destroy': (c_int, [c_void_p]),
-    'dmlb_comm_allreduce': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p, c_int, c_void_p]),
+    'dmlb_comm_configure': (c_int, [c_void_p, c_double, c_void_p]),
+    'dmlb_comm_set_multicast': (c_int, [c_void_p, c_void_p]),
+    'dmlb_comm_allreduce': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p, c_int, POINTER(StepMetrics),
+                                    c_void_p]),
+    'dmlb_vmm_granularity': (c_size_t, [c_int, c_int]),
+    'dmlb_vmm_alloc': (c_int, [c_int, c_size_t, POINTER(c_void_p), POINTER(c_int), POINTER(c_uint64)]),
+    'dmlb_vmm_import': (c_int, [c_int, c_int, c_size_t, POINTER(c_void_p), POINTER(c_uint64)]),
+    'dmlb_vmm_free': (c_int, [c_void_p, c_size_t, c_uint64]),
+    'dmlb_mc_create': (c_int, [c_int, c_size_t, POINTER(c_int), POINTER(c_uint64)]),
+    'dmlb_mc_import': (c_int, [c_int, POINTER(c_uint64)]),
+    'dmlb_mc_add_device': (c_int, [c_uint64, c_int]),
+    'dmlb_mc_bind': (c_int, [c_uint64, c_int, c_uint64, c_size_t, POINTER(c_void_p)]),
+    'dmlb_mc_release': (c_int, [c_uint64, c_void_p, c_size_t]),
     'dmlb_comm_barrier': (c_int, [c_void_p, c_void_p]),
     'dmlb_comm_error': (c_int, [c_void_p, POINTER(c_int)]),
     'dmlb_metric_reset': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'dmlb_metric_fold': (c_int, [c_void_p, c_void_p, c_void_p, POINTER(FoldEntry), c_int, c_void_p]),
-    'dmlb_metric_reduce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(Range), c_int, c_uint64,
+    'dmlb_metric_reduce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(Range), c_int, c_int, c_uint64,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'dmlb_metric_finalize': (c_int, [c_void_p, c_void_p, c_void_p, POINTER(Range), c_int, c_uint64, c_int, c_void_p,
                                      c_void_p]),
@@ -114,7 +142,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = restype
                 fn.argtypes = argtypes
-            if lib.dmlb_abi_version() != 1:
+            if lib.dmlb_abi_version() != ABI_VERSION:
                 raise RuntimeError('libdmlb ABI version mismatch; rebuild with python -m dmlcloud_b200.csrc.build')
             _lib = lib
     return _lib

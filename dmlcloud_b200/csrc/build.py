@@ -12,8 +12,8 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SOURCES = ['core.cu', 'bucket_kernels.cu', 'bucket_tma.cu', 'peer_comm.cu', 'metric_kernels.cu', 'shard_kernels.cu',
-           'optim_kernels.cu']
-HEADERS = ['dmlb_common.cuh', 'peer_comm.cuh', '../../include/dmlb.h']
+           'optim_kernels.cu', 'vmm.cu']
+HEADERS = ['dmlb_common.cuh', 'peer_comm.cuh', 'metric_dev.cuh', '../../include/dmlb.h']
 LIB = HERE / 'libdmlb.so'
 STAMP = HERE / '.libdmlb.stamp'
 

@@ -1,23 +1,32 @@
-// Fused gradient-bucket all-reduce over NVLink 5 / NVSwitch peer memory (sm_100a).
+// Fused gradient-bucket all-reduce + per-step metric exchange over NVLink 5 / NVSwitch peer memory (sm_100a).
 //
 // Replaces, for one DDP bucket, the chain the reference runs through torch (pipeline.py:74 -> Reducer -> c10d):
 //     bucket * (1/W)  [-> bf16]   ->   allreduce(SUM)   ->   [bf16 ->] fp32 copy back into .grad
-// with ONE kernel: scale+cast into this rank's staging half (K1), flag barrier through peer-mapped memory, rank-ordered
-// fp32 sum over every rank's staging read across NVLink (the collective), write-back into the fp32 bucket (K2), plus
-// an optional fused sum of squares for gradient clipping.  No NCCL, no host round trip, CUDA-graph capturable (the
-// sequence number lives in device memory).
+// with ONE kernel: scale+cast into this rank's staging half (K1), flag barrier through peer-mapped memory, fp32 sum over
+// every rank's staging read across NVLink (the collective), write-back into the fp32 bucket (K2), plus an optional
+// fused sum of squares for gradient clipping.  No NCCL, no host round trip, CUDA-graph capturable (the sequence number
+// lives in device memory).
 //
 //   one-shot  (message <= oneshot_max):  every rank reads all W staging buffers  — (W-1)*M bytes over NVLink per GPU,
 //                                        one barrier; latency-optimal for the 41 KB MNIST bucket.
-//   two-shot  (larger):                  reduce-scatter then all-gather through peer memory — 2*(W-1)/W*M bytes per
-//                                        GPU, two barriers; bandwidth-optimal for ResNet-18's 1.96/27.5/15.1 MiB buckets.
+//   two-shot  (larger):                  reduce-scatter then all-gather through peer loads — 2*(W-1)/W*M bytes per GPU,
+//                                        two barriers.
+//   NVLS      (larger, multicast bound): multimem.ld_reduce pulls this rank's 1/W slice already SUMMED BY THE SWITCH,
+//                                        multimem.st broadcasts it — (1 + 1/W)*M bytes per GPU and direction, two barriers.
 //
-// Numerics: fp32 accumulate in rank order 0..W-1 on every rank => results are bit-identical across ranks and equal to
-// oracle/grad_oracle.py allreduce_f32 / allreduce_bf16.  Two-shot with the bf16 wire rounds the sum to bf16 for the
-// all-gather phase (same as an NCCL bf16 all-reduce); the fp32 wire is exact in both algorithms.
-#include <cstdlib>
+// The fused STEP EXCHANGE: when a dmlb_step_metrics descriptor is attached, one extra CTA of the same kernel folds the
+// step's tracked values into the metric slab, finalises the selected cells, exchanges 16-byte records under the SAME flag
+// barrier as the gradients and writes the cross-rank results into a ring in mapped host memory — the reference's
+// per-step `track_reduce` traffic (stage.py:305-314) and its cross-rank reduction (metrics.py:121-141) cost no launch
+// and no barrier of their own.
+//
+// Numerics: one-shot / two-shot accumulate in fp32 in rank order 0..W-1 on every rank => results are bit-identical
+// across ranks and equal to oracle/grad_oracle.py allreduce_f32 / allreduce_bf16.  Two-shot and NVLS with the bf16 wire
+// round the sum to bf16 for the all-gather phase (same as an NCCL bf16 all-reduce).  NVLS sums in the switch (fp32
+// accumulation, order fixed by the hardware, identical on all ranks because every rank receives the same broadcast).
 #include <new>
 
+#include "metric_dev.cuh"
 #include "peer_comm.cuh"
 
 namespace dmlb {
@@ -37,6 +46,14 @@ struct Wire<DMLB_WIRE_F32> {  // 4 elements per 16-byte wire vector
         acc[0] += __uint_as_float(w.x), acc[1] += __uint_as_float(w.y);
         acc[2] += __uint_as_float(w.z), acc[3] += __uint_as_float(w.w);
     }
+    __device__ static __forceinline__ uint4 mc_reduce(const void *mc) {  // in-switch sum over all ranks' copies
+        uint4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(mc)
+                     : "memory");
+        return v;
+    }
 };
 
 template <>
@@ -52,7 +69,20 @@ struct Wire<DMLB_WIRE_BF16> {  // 8 elements per 16-byte wire vector
         acc[0] += bf16_lo(w.x), acc[1] += bf16_hi(w.x), acc[2] += bf16_lo(w.y), acc[3] += bf16_hi(w.y);
         acc[4] += bf16_lo(w.z), acc[5] += bf16_hi(w.z), acc[6] += bf16_lo(w.w), acc[7] += bf16_hi(w.w);
     }
+    __device__ static __forceinline__ uint4 mc_reduce(const void *mc) {  // fp32 accumulation in the switch, bf16 result
+        uint4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(mc)
+                     : "memory");
+        return v;
+    }
 };
+
+__device__ __forceinline__ void mc_store(void *mc, uint4 v) {  // one store, delivered to every rank's copy
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
 
 // load kElems fp32 bucket elements of wire vector g (guarded at the ragged end), scaled
 template <int E>
@@ -93,45 +123,49 @@ __device__ __forceinline__ double store_bucket(float *bucket, size_t g, size_t n
     return p;
 }
 
+// A peer did not arrive: overwrite this CTA's part of the bucket with NaN so that nobody trains on a partial sum.
+template <int E>
+__device__ __forceinline__ void poison_range(float *bucket, size_t lo, size_t hi, size_t n) {
+    const float nan = __int_as_float(0x7fc00000);
+    for (size_t e = lo * E + threadIdx.x; e < hi * E && e < n; e += kCommThreads) bucket[e] = nan;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Memory-level parallelism.  A peer load over NVLink takes ~2-3 us; to keep 770 GB/s busy ~2 MB must be in flight per
 // GPU.  With <= 296 x 256 threads that means several independent 16-byte loads per thread: every loop below gathers
 // kU vectors x W ranks into registers before the first add (kU = 4 for W <= 2, 2 for W <= 4, 1 for W <= 8 keeps the
 // register budget at ~32 data registers).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kWire, int kU, int kStride = kCommThreads>
-__device__ __forceinline__ double pack_range(const CommDev &c, const float *bucket, uint4 *mine, size_t lo, size_t hi,
-                                             size_t n, float scale, int tid = threadIdx.x) {
+template <int kWire, int kU>
+__device__ __forceinline__ void pack_range(const float *bucket, uint4 *mine, size_t lo, size_t hi, size_t n, float scale) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
-    for (size_t g0 = lo + tid; g0 < hi; g0 += (size_t)kStride * kU) {
+    for (size_t g0 = lo + threadIdx.x; g0 < hi; g0 += (size_t)kCommThreads * kU) {
         float v[kU][E];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t g = g0 + (size_t)u * kStride;
+            const size_t g = g0 + (size_t)u * kCommThreads;
             if (g < hi) load_bucket<E>(bucket, g, n, scale, v[u]);
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t g = g0 + (size_t)u * kStride;
+            const size_t g = g0 + (size_t)u * kCommThreads;
             if (g < hi) mine[g] = W::pack(v[u]);
         }
     }
-    return 0.0;
 }
 
 // out(g) = sum over ranks of stage[r][g] for g in [lo, hi) (index space of the staging buffers, offset `goff`)
-template <int kWire, int kU, int kStride = kCommThreads, class Sink>
-__device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t lo, size_t hi, size_t goff, Sink sink,
-                                             int tid = threadIdx.x) {
+template <int kWire, int kU, class Sink>
+__device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t lo, size_t hi, size_t goff, Sink sink) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
     constexpr int kMaxW = DMLB_MAX_WORLD / kU;  // the host picks kU so that world <= kMaxW: kU x kMaxW = 8 vectors in flight
-    for (size_t i0 = lo + tid; i0 < hi; i0 += (size_t)kStride * kU) {
+    for (size_t i0 = lo + threadIdx.x; i0 < hi; i0 += (size_t)kCommThreads * kU) {
         uint4 w[kU][kMaxW];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t i = i0 + (size_t)u * kStride;
+            const size_t i = i0 + (size_t)u * kCommThreads;
             if (i < hi) {
 #pragma unroll
                 for (int r = 0; r < kMaxW; ++r)
@@ -140,7 +174,7 @@ __device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t 
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const size_t i = i0 + (size_t)u * kStride;
+            const size_t i = i0 + (size_t)u * kCommThreads;
             if (i < hi) {
                 float acc[E];
 #pragma unroll
@@ -155,28 +189,160 @@ __device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The metric CTA of the fused step exchange (block index == number of data CTAs).
+// fold -> finalise (no reset) -> records into mstage[half] -> the collective's barrier 0 -> rank-ordered combine -> ring.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void metric_cta(const CommDev &c, uint32_t s, const dmlb_step_metrics &M) {
+    __shared__ unsigned long long s_count;
+    long long *cnt = reinterpret_cast<long long *>(M.cnt);
+    if (threadIdx.x == 0) s_count = *reinterpret_cast<volatile unsigned long long *>(M.counter);
+    __syncthreads();
+    const unsigned long long count = s_count;
+    const bool exchange = c.world > 1;
+    const int half = s & 1;
+
+    // 1. this step's values: warp w takes entries w, w + 8, ...
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const double *feed_slot = (M.feed && M.feed_slots > 0)
+                                      ? M.feed + (size_t)(count % (unsigned long long)M.feed_slots) * 2 * DMLB_FEED_WIDTH
+                                      : nullptr;
+        for (int j = warp; j < M.n_folds; j += kCommThreads / 32) {
+            dmlb_fold_entry e = M.folds[j];
+            if (e.src_dtype == DMLB_SRC_FEED) {
+                if (!feed_slot) continue;
+                e.src = feed_slot;
+            }
+            fold_entry(M.acc, cnt, M.desc, e, lane, 32);
+        }
+    }
+    __syncthreads();  // entries may target cells the finalisation below reads (same CTA: block-level ordering is enough)
+
+    // 2. finalise
+    unsigned char *slot = M.out_ring + (size_t)(count % (unsigned long long)M.ring_slots) *
+                                           ((size_t)DMLB_METRIC_STATUS_SLOTS * 4 + 9 * (size_t)M.capacity);
+    int *status = reinterpret_cast<int *>(slot);
+    uint64_t *out_val = reinterpret_cast<uint64_t *>(slot + DMLB_METRIC_STATUS_SLOTS * 4);
+    uint8_t *out_flag = slot + DMLB_METRIC_STATUS_SLOTS * 4 + 8 * (size_t)M.capacity;
+    int n_glob = 0, n_all = 0;
+    for (int j = 0; j < M.n_ranges; ++j) {
+        const int len = M.ranges[j].end - M.ranges[j].begin;
+        n_all += len;
+        if (j < M.n_global_ranges) n_glob += len;
+    }
+    const dmlb_range *lr = M.ranges + M.n_global_ranges;
+    for (int i = threadIdx.x; i < n_all - n_glob; i += kCommThreads) {
+        const int cell = sel_to_cell(lr, M.n_ranges - M.n_global_ranges, i);
+        uint64_t val;
+        long long n;
+        finalize_cell(M.acc, cnt, M.desc[cell], cell, val, n, false);
+        out_val[cell] = val;
+        out_flag[cell] = n > 0 ? 0 : 1;
+    }
+    uint64_t *rec_mine = reinterpret_cast<uint64_t *>(c.mstage(c.rank, half));
+    for (int i = threadIdx.x; i < n_glob; i += kCommThreads) {
+        const int cell = sel_to_cell(M.ranges, M.n_global_ranges, i);
+        uint64_t val;
+        long long n;
+        finalize_cell(M.acc, cnt, M.desc[cell], cell, val, n, false);
+        if (exchange) {
+            rec_mine[2 + 2 * i] = val;
+            rec_mine[3 + 2 * i] = (uint64_t)n;
+        } else {
+            out_val[cell] = val;
+            out_flag[cell] = n > 0 ? 0 : 1;
+        }
+    }
+    int st = DMLB_METRIC_OK;
+    if (exchange) {
+        if (threadIdx.x == 0) {
+            rec_mine[0] = M.layout_hash;
+            rec_mine[1] = (uint64_t)n_glob;
+        }
+        // 3. the collective's barrier 0 (this CTA owns flag slot blockIdx.x like any data CTA)
+        const bool arrived = comm_barrier(c, 0, s);
+        if (!arrived) st = DMLB_METRIC_TIMEOUT;
+        if (arrived && threadIdx.x < c.world) {
+            uint4 h = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.mstage(threadIdx.x, half)));
+            const uint64_t ph = ((uint64_t)h.y << 32) | h.x, pn = ((uint64_t)h.w << 32) | h.z;
+            if (ph != M.layout_hash || pn != (uint64_t)n_glob) st = DMLB_METRIC_LAYOUT;
+        }
+        const bool ok = __syncthreads_or(st != DMLB_METRIC_OK) == 0;
+        // 4. combine in rank order
+        if (ok)
+            for (int i = threadIdx.x; i < n_glob; i += kCommThreads) {
+                const int cell = sel_to_cell(M.ranges, M.n_global_ranges, i);
+                uint64_t out;
+                uint8_t flag;
+                auto rec = [&](int r, uint64_t &v, long long &n) {
+                    uint4 w = ld_coherent_u4(reinterpret_cast<const uint4 *>(c.mstage(r, half)) + 1 + i);
+                    v = ((uint64_t)w.y << 32) | w.x;
+                    n = (long long)(((uint64_t)w.w << 32) | w.z);
+                };
+                combine_cell(M.desc[cell], c.world, rec, out, flag, st);
+                out_val[cell] = out;
+                out_flag[cell] = flag;
+            }
+    }
+    int worst = DMLB_METRIC_OK;
+    if (__syncthreads_or(st == DMLB_METRIC_TIMEOUT)) worst = DMLB_METRIC_TIMEOUT;
+    else if (__syncthreads_or(st == DMLB_METRIC_LAYOUT)) worst = DMLB_METRIC_LAYOUT;
+    else if (__syncthreads_or(st == DMLB_METRIC_SPLIT_VOTE)) worst = DMLB_METRIC_SPLIT_VOTE;
+    // 5. publish: results first, then the stamp (the host trusts a slot only when its stamp matches)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        status[0] = worst;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(slot + DMLB_METRIC_STATUS_SLOTS * 4 - 8) = count + 1ull;
+        *reinterpret_cast<volatile unsigned long long *>(M.counter) = count + 1ull;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // one-shot
 // ---------------------------------------------------------------------------------------------------------------------
 template <int kWire, int kU>
 __global__ void __launch_bounds__(kCommThreads, 2)
 allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, float scale,
-                         double *sumsq_out) {
+                         double *sumsq_out, int n_data, const __grid_constant__ dmlb_step_metrics M) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
     const uint32_t s = comm_begin(c);
+    if ((int)blockIdx.x >= n_data) {
+        metric_cta(c, s, M);
+        comm_end(c, s);
+        return;
+    }
     const int half = s & 1;
-    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    const size_t per = (nvec + n_data - 1) / n_data;
     const size_t lo = (size_t)blockIdx.x * per;
     const size_t hi = min(nvec, lo + per);
-
-    pack_range<kWire, kU>(c, bucket, reinterpret_cast<uint4 *>(c.stage(c.rank, half)), lo, hi, n, scale);
-    comm_barrier(c, 0, s);
-
     double part = 0.0;
     const bool want_sumsq = sumsq_out != nullptr;
-    reduce_range<kWire, kU>(c, half, lo, hi, 0, [&](size_t g, const float *acc) {
-        part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
-    });
+
+    if (c.world == 1) {
+        // nobody to exchange with: round through the wire dtype in registers (what pack -> sum over one rank -> unpack
+        // computes), no staging, no barrier
+        for (size_t g = lo + threadIdx.x; g < hi; g += kCommThreads) {
+            float v[E], acc[E];
+            load_bucket<E>(bucket, g, n, scale, v);
+            const uint4 w = W::pack(v);
+#pragma unroll
+            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+            W::accumulate(acc, w);
+            part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
+        }
+    } else {
+        pack_range<kWire, kU>(bucket, reinterpret_cast<uint4 *>(c.stage(c.rank, half)), lo, hi, n, scale);
+        if (comm_barrier(c, 0, s)) {
+            reduce_range<kWire, kU>(c, half, lo, hi, 0, [&](size_t g, const float *acc) {
+                part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
+            });
+        } else {
+            poison_range<E>(bucket, lo, hi, n);
+            part = __longlong_as_double(0x7ff8000000000000ll);
+        }
+    }
     if (sumsq_out) {
         double tot = block_sum(part);
         if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
@@ -185,92 +351,26 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// one-shot, tile-pipelined: the CTA's range is cut into chunks; warps 0-3 only pack (HBM: read fp32, write wire dtype),
-// warps 4-7 only reduce (NVLink: read every rank's staging chunk, sum, write fp32).  Chunk k+1 is being packed while the
-// peers' chunk k crosses NVLink, so the HBM pass and the NVLink pass overlap INSIDE the kernel instead of running as two
-// phases.  Per-chunk flags live in flag region 2 with values (s << 8) | (k + 1): monotonic across collectives, so the
-// ">= target" test of the non-pipelined kernels carries over; the staging double buffer gives the same WAR guarantee.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kRole = 128;  // threads per role
-__device__ __forceinline__ void role_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kRole) : "memory"); }
-
-template <int kWire, int kU>
-__global__ void __launch_bounds__(2 * kRole, 2)
-allreduce_oneshot_pipelined_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec,
-                                   size_t chunk, float scale, double *sumsq_out) {
-    typedef Wire<kWire> W;
-    constexpr int E = W::kElems;
-    const uint32_t s = comm_begin(c);
-    const int half = s & 1;
-    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
-    const size_t lo = (size_t)blockIdx.x * per;
-    const size_t hi = min(nvec, lo + per);
-    const int n_chunks = hi > lo ? (int)((hi - lo + chunk - 1) / chunk) : 0;
-    const uint32_t base = s << 8;
-    const bool reducer = threadIdx.x >= kRole;
-    const int tid = threadIdx.x & (kRole - 1);
-
-    if (!reducer) {
-        uint4 *mine = reinterpret_cast<uint4 *>(c.stage(c.rank, half));
-        for (int k = 0; k < n_chunks; ++k) {
-            const size_t clo = lo + (size_t)k * chunk, chi = min(hi, clo + chunk);
-            pack_range<kWire, kU, kRole>(c, bucket, mine, clo, chi, n, scale, tid);
-            __threadfence_system();
-            role_sync(1);
-            if (tid < c.world) st_release_sys(c.flags(tid, 2, blockIdx.x) + c.rank, base + (uint32_t)k + 1u);
-        }
-    } else {
-        double part = 0.0;
-        const bool want_sumsq = sumsq_out != nullptr;
-        for (int k = 0; k < n_chunks; ++k) {
-            const size_t clo = lo + (size_t)k * chunk, chi = min(hi, clo + chunk);
-            if (tid < c.world) {
-                const uint32_t *mine = c.flags(c.rank, 2, blockIdx.x) + tid;
-                const uint32_t target = base + (uint32_t)k + 1u;
-                const unsigned long long t0 = globaltimer_ns();
-                while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {
-                    if (globaltimer_ns() - t0 > c.timeout_ns) {
-                        atomicExch(c.err(), 1u);
-                        break;
-                    }
-                }
-            }
-            role_sync(2);
-            reduce_range<kWire, kU, kRole>(c, half, clo, chi, 0, [&](size_t g, const float *acc) {
-                part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
-            }, tid);
-        }
-        if (want_sumsq) {  // reduce over the 4 reducer warps only
-            __shared__ double s_red[kRole / 32];
-            part = warp_sum(part);
-            if ((tid & 31) == 0) s_red[tid >> 5] = part;
-            role_sync(2);
-            if (tid == 0) {
-                double tot = 0.0;
-                for (int w = 0; w < kRole / 32; ++w) tot += s_red[w];
-                if (tot != 0.0) atomicAdd(sumsq_out, tot);
-            }
-        }
-    }
-    comm_end(c, s);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // two-shot: slice q (S wire vectors) is reduced by rank q.  CTA b owns vector range [b*per, (b+1)*per) of EVERY slice,
 // so it only ever depends on what the peers' CTA b wrote (per-CTA barriers suffice).
+// kNvls: the reduce-scatter + all-gather pair is done by the switch — multimem.ld_reduce of my slice from the multicast
+// mapping of all staging halves, multimem.st of the sum back into every rank's staging half (in place: between the two
+// barriers only the owner touches slice q), then every rank widens its own, now reduced, staging half.
 // ---------------------------------------------------------------------------------------------------------------------
-// kPush: the all-gather half is PUSHED — the rank that reduced a slice stores it into every rank's result half (posted
-// NVLink writes that overlap the reduce-scatter's pulls, which use the other link direction), and after the second
-// barrier every rank widens from its LOCAL copy at HBM speed.  !kPush: peers pull the slices after the second barrier.
-template <int kWire, int kU, bool kPush>
+template <int kWire, int kU, bool kNvls>
 __global__ void __launch_bounds__(kCommThreads, 2)
 allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S, float scale,
-                         double *sumsq_out) {
+                         double *sumsq_out, int n_data, const __grid_constant__ dmlb_step_metrics M) {
     typedef Wire<kWire> W;
     constexpr int E = W::kElems;
     const uint32_t s = comm_begin(c);
+    if ((int)blockIdx.x >= n_data) {
+        metric_cta(c, s, M);
+        comm_end(c, s);
+        return;
+    }
     const int half = s & 1;
-    const size_t per = (S + gridDim.x - 1) / gridDim.x;
+    const size_t per = (S + n_data - 1) / n_data;
     const size_t lo = (size_t)blockIdx.x * per;
     const size_t hi = min(S, lo + per);
 
@@ -279,283 +379,71 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     for (int q = 0; q < c.world; ++q) {
         const size_t off = (size_t)q * S;
         if (off >= nvec) break;
-        pack_range<kWire, kU>(c, bucket, mine, off + lo, min(off + hi, nvec), n, scale);
+        pack_range<kWire, kU>(bucket, mine, off + lo, min(off + hi, nvec), n, scale);
     }
-    comm_barrier(c, 0, s);
+    bool ok = comm_barrier(c, 0, s);
 
-    // phase 2 (reduce-scatter): I reduce slice `rank` from every peer's staging — into my result half (pull variant:
-    // slice-local index) or into every rank's result half (push variant: global vector index)
+    // phase 2 (reduce-scatter): I reduce slice `rank`
     constexpr int kMaxW = DMLB_MAX_WORLD / kU;
     {
-        uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
         const size_t off = (size_t)c.rank * S;
         const size_t lim = off < nvec ? min(hi, nvec - off) : 0;
-        if (lo < lim) {
-            if (kPush)
-                reduce_range<kWire, kU>(c, half, lo, lim, off, [&](size_t i, const float *acc) {
-                    const uint4 v = W::pack(acc);
+        if (ok && lo < lim) {
+            if (kNvls) {
+                unsigned char *mcs = c.mc_stage(half) + off * 16;
+                constexpr int kV = 4;  // independent in-switch reductions in flight per thread
+                for (size_t i0 = lo + threadIdx.x; i0 < lim; i0 += (size_t)kCommThreads * kV) {
+                    uint4 v[kV];
 #pragma unroll
-                    for (int r = 0; r < kMaxW; ++r)
-                        if (r < c.world) reinterpret_cast<uint4 *>(c.result(r, half))[off + i] = v;
-                });
-            else
+                    for (int u = 0; u < kV; ++u) {
+                        const size_t i = i0 + (size_t)u * kCommThreads;
+                        if (i < lim) v[u] = W::mc_reduce(mcs + i * 16);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kV; ++u) {
+                        const size_t i = i0 + (size_t)u * kCommThreads;
+                        if (i < lim) mc_store(mcs + i * 16, v[u]);
+                    }
+                }
+            } else {
+                uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
                 reduce_range<kWire, kU>(c, half, lo, lim, off, [&](size_t i, const float *acc) { res[i] = W::pack(acc); });
-        }
-    }
-    comm_barrier(c, 1, s);
-
-    // phase 3 (all-gather + K2): W loads in flight per thread — from every rank's reduced slice over NVLink (pull) or
-    // from this rank's own, already complete, result half (push) — widened into the bucket
-    double part = 0.0;
-    const bool want_sumsq = sumsq_out != nullptr;
-    for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
-        uint4 w[kMaxW];
-#pragma unroll
-        for (int q = 0; q < kMaxW; ++q)
-            if (q < c.world && (size_t)q * S + i < nvec)
-                w[q] = kPush ? ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(c.rank, half)) + (size_t)q * S + i)
-                             : ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
-#pragma unroll
-        for (int q = 0; q < kMaxW; ++q) {
-            const size_t g = (size_t)q * S + i;
-            if (q < c.world && g < nvec) {
-                float acc[E];
-#pragma unroll
-                for (int j = 0; j < E; ++j) acc[j] = 0.0f;
-                W::accumulate(acc, w[q]);
-                part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
             }
         }
+    }
+    ok = comm_barrier(c, 1, s) && ok;
+
+    // phase 3 (all-gather + K2): W loads in flight per thread — from every rank's reduced slice over NVLink (pull), or
+    // (NVLS) from my own staging half, which the owners' multicast stores have overwritten with the sums
+    double part = 0.0;
+    const bool want_sumsq = sumsq_out != nullptr;
+    if (ok) {
+        for (size_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
+            uint4 w[kMaxW];
+#pragma unroll
+            for (int q = 0; q < kMaxW; ++q)
+                if (q < c.world && (size_t)q * S + i < nvec)
+                    w[q] = kNvls ? ld_coherent_u4(reinterpret_cast<const uint4 *>(mine) + (size_t)q * S + i)
+                                 : ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
+#pragma unroll
+            for (int q = 0; q < kMaxW; ++q) {
+                const size_t g = (size_t)q * S + i;
+                if (q < c.world && g < nvec) {
+                    float acc[E];
+#pragma unroll
+                    for (int j = 0; j < E; ++j) acc[j] = 0.0f;
+                    W::accumulate(acc, w[q]);
+                    part += store_bucket<E>(bucket, g, n, acc, want_sumsq);
+                }
+            }
+        }
+    } else {
+        for (int q = 0; q < c.world; ++q) poison_range<E>(bucket, (size_t)q * S + lo, min((size_t)q * S + hi, nvec), n);
+        part = __longlong_as_double(0x7ff8000000000000ll);
     }
     if (sumsq_out) {
         double tot = block_sum(part);
         if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
-    }
-    comm_end(c, s);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// two-shot, PUSH-pipelined (algo 5).  Every NVLink transfer is a posted store, every load is local:
-//
-//   A(t)  pack chunk t of every slice q and store it into rank q's staging half at [my rank][i]      (scatter push)
-//   B(t)  sum the W contributions of my slice's chunk t from my LOCAL staging half (rank order), cast,
-//         store the reduced vectors into every rank's result half at the global index                 (gather push)
-//   C(t)  widen chunk t of every slice from my LOCAL result half into the fp32 bucket (+ sum of squares)
-//
-// A thread never waits for an NVLink round trip: peer loads (the latency x parallelism limit of the pull kernels) are
-// gone, and the links stay busy while the HBM passes run.  The six worker warps of a CTA run A(t), B(t-1), C(t-2)
-// back to back; two control warps (one for stage A, one for stage B) do all the signalling so that the system-scope
-// fence before a flag store (which waits for the pushes to be acknowledged) never stalls a worker:
-//   workers  -> control : shared-memory arrival counter per stage (release: __syncwarp + fence.cta + atomicAdd)
-//   control  -> peers   : fence.sys + st.release.sys of (s << 8 | t + 1) into flag region 2 (A) / 3 (B), per CTA
-//   peers    -> control : ld.acquire.sys polling of this CTA's own flag words
-//   control  -> workers : shared-memory "chunks ready" counter per stage
-// WAR safety is the double buffer again: a peer can only be in collective s+1 (writing the other half of my arena)
-// once all my CTAs have finished stages A and B of s, and it cannot finish s+1 before I have taken part in it.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kCtrlWarps = 2;
-constexpr int kWorkerWarps = kCommThreads / 32 - kCtrlWarps;
-constexpr int kWorkers = kWorkerWarps * 32;
-
-struct PushShared {
-    uint32_t done[2];   // worker warps that finished stage X of (done / kWorkerWarps) chunks
-    uint32_t ready[2];  // chunks of stage X whose data from every rank has landed in this rank's arena
-};
-
-__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
-
-template <int kWire, int kU>
-__global__ void __launch_bounds__(kCommThreads, 2)
-allreduce_push_pipelined_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S,
-                                size_t chunk, float scale, double *sumsq_out) {
-    typedef Wire<kWire> W;
-    constexpr int E = W::kElems;
-    constexpr int kMaxW = DMLB_MAX_WORLD / kU;
-    constexpr int kUA = 16 / E;  // wire vectors per worker thread per iteration of stages A and C: four 128-bit bucket loads in flight
-    __shared__ PushShared sh;
-    __shared__ double s_red[kWorkerWarps];
-    if (threadIdx.x == 0) sh.done[0] = sh.done[1] = sh.ready[0] = sh.ready[1] = 0u;
-    const uint32_t s = comm_begin(c);  // (contains the __syncthreads that publishes the zeroed counters)
-    const int half = s & 1;
-    const size_t per = (S + gridDim.x - 1) / gridDim.x;
-    const size_t lo = (size_t)blockIdx.x * per;
-    const size_t hi = min(S, lo + per);
-    const int K = hi > lo ? (int)((hi - lo + chunk - 1) / chunk) : 0;
-    const uint32_t base = s << 8;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double part = 0.0;
-
-    if (warp < kCtrlWarps) {
-        // ---- control warp of stage X: lane r talks to rank r ----
-        const int X = warp;
-        const int region = 2 + X;
-        int sig = 0, rdy = 0;
-        const unsigned long long t0 = globaltimer_ns();
-        while (sig < K || rdy < K) {
-            if (sig < K) {
-                uint32_t d = 0;
-                if (lane == 0) {
-                    d = ld_volatile_shared(&sh.done[X]);
-                    __threadfence_block();
-                }
-                d = __shfl_sync(0xffffffffu, d, 0);
-                __syncwarp();
-                if (d >= (uint32_t)kWorkerWarps * (uint32_t)(sig + 1)) {  // every worker warp has issued chunk `sig`
-                    if (lane < c.world) {
-                        __threadfence_system();  // cumulative: the workers' pushes are ordered before the flag
-                        st_release_sys(c.flags(lane, region, blockIdx.x) + c.rank, base + (uint32_t)sig + 1u);
-                    }
-                    ++sig;
-                }
-            }
-            if (rdy < K) {
-                bool ok = true;
-                if (lane < c.world)
-                    ok = (int32_t)(ld_acquire_sys(c.flags(c.rank, region, blockIdx.x) + lane) - (base + (uint32_t)rdy + 1u)) >= 0;
-                if (__all_sync(0xffffffffu, ok)) {
-                    __syncwarp();
-                    ++rdy;
-                    if (lane == 0) {
-                        __threadfence_block();
-                        *reinterpret_cast<volatile uint32_t *>(&sh.ready[X]) = (uint32_t)rdy;
-                    }
-                }
-            }
-            if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > c.timeout_ns)) {  // a peer died: record it, release the workers, stop
-                if (lane == 0) {
-                    atomicExch(c.err(), 1u);
-                    *reinterpret_cast<volatile uint32_t *>(&sh.ready[X]) = (uint32_t)K;
-                }
-                break;
-            }
-        }
-    } else {
-        const int w = threadIdx.x - kCtrlWarps * 32;
-        const bool want_sumsq = sumsq_out != nullptr;
-        const uint4 *my_stage = reinterpret_cast<const uint4 *>(c.stage(c.rank, half));
-        const uint4 *my_result = reinterpret_cast<const uint4 *>(c.result(c.rank, half));
-        auto arrive = [&](int X) {
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                atomicAdd(&sh.done[X], 1u);
-            }
-        };
-        auto await = [&](int X, int chunks) {
-            if (lane == 0)
-                while (ld_volatile_shared(&sh.ready[X]) < (uint32_t)chunks) {}
-            __syncwarp();
-            __threadfence_block();
-        };
-        for (int t = 0; t < K + 2; ++t) {
-            if (t < K) {  // ---- A(t): scale + cast, scatter to the slice owners ----
-                const size_t clo = lo + (size_t)t * chunk;
-                const uint32_t cw = (uint32_t)(min(hi, clo + chunk) - clo);
-                const uint32_t items = cw * (uint32_t)c.world;
-                for (uint32_t j0 = w; j0 < items; j0 += kWorkers * kUA) {
-                    float v[kUA][E];
-                    size_t idx[kUA];
-                    int owner[kUA];
-#pragma unroll
-                    for (int u = 0; u < kUA; ++u) {
-                        const uint32_t j = j0 + u * kWorkers;
-                        owner[u] = -1;
-                        if (j < items) {
-                            const uint32_t q = j / cw;
-                            const size_t i = clo + (j - q * cw);
-                            const size_t g = (size_t)q * S + i;
-                            if (g < nvec) {
-                                owner[u] = (int)q;
-                                idx[u] = (size_t)c.rank * S + i;
-                                load_bucket<E>(bucket, g, n, scale, v[u]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kUA; ++u)
-                        if (owner[u] >= 0) reinterpret_cast<uint4 *>(c.stage(owner[u], half))[idx[u]] = W::pack(v[u]);
-                }
-                arrive(0);
-            }
-            if (t >= 1 && t - 1 < K) {  // ---- B(t-1): reduce my slice's chunk locally, push it to everyone ----
-                await(0, t);
-                const size_t clo = lo + (size_t)(t - 1) * chunk;
-                const size_t chi = min(hi, clo + chunk);
-                const size_t off = (size_t)c.rank * S;
-                const size_t lim = off < nvec ? min(chi, nvec - off) : 0;
-                for (size_t i0 = clo + w; i0 < lim; i0 += (size_t)kWorkers * kU) {
-                    uint4 x[kU][kMaxW];
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const size_t i = i0 + (size_t)u * kWorkers;
-                        if (i < lim) {
-#pragma unroll
-                            for (int r = 0; r < kMaxW; ++r)
-                                if (r < c.world) x[u][r] = ld_coherent_u4(my_stage + (size_t)r * S + i);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const size_t i = i0 + (size_t)u * kWorkers;
-                        if (i < lim) {
-                            float acc[E];
-#pragma unroll
-                            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
-#pragma unroll
-                            for (int r = 0; r < kMaxW; ++r)
-                                if (r < c.world) W::accumulate(acc, x[u][r]);
-                            const uint4 red = W::pack(acc);
-#pragma unroll
-                            for (int r = 0; r < kMaxW; ++r)
-                                if (r < c.world) reinterpret_cast<uint4 *>(c.result(r, half))[off + i] = red;
-                        }
-                    }
-                }
-                arrive(1);
-            }
-            if (t >= 2) {  // ---- C(t-2): widen every slice's chunk from my local result half ----
-                await(1, t - 1);
-                const size_t clo = lo + (size_t)(t - 2) * chunk;
-                const uint32_t cw = (uint32_t)(min(hi, clo + chunk) - clo);
-                const uint32_t items = cw * (uint32_t)c.world;
-                for (uint32_t j0 = w; j0 < items; j0 += kWorkers * kUA) {
-                    uint4 x[kUA];
-                    size_t gi[kUA];
-#pragma unroll
-                    for (int u = 0; u < kUA; ++u) {
-                        const uint32_t j = j0 + u * kWorkers;
-                        gi[u] = nvec;
-                        if (j < items) {
-                            const uint32_t q = j / cw;
-                            const size_t g = (size_t)q * S + clo + (j - q * cw);
-                            if (g < nvec) {
-                                gi[u] = g;
-                                x[u] = ld_coherent_u4(my_result + g);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kUA; ++u)
-                        if (gi[u] < nvec) {
-                            float acc[E];
-#pragma unroll
-                            for (int j = 0; j < E; ++j) acc[j] = 0.0f;
-                            W::accumulate(acc, x[u]);
-                            part += store_bucket<E>(bucket, gi[u], n, acc, want_sumsq);
-                        }
-                }
-            }
-        }
-        if (want_sumsq) {
-            part = warp_sum(part);
-            if (lane == 0) s_red[warp - kCtrlWarps] = part;
-        }
-    }
-    __syncthreads();
-    if (sumsq_out && threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int i = 0; i < kWorkerWarps; ++i) tot += s_red[i];
-        if (tot != 0.0) atomicAdd(sumsq_out, tot);
     }
     comm_end(c, s);
 }
@@ -567,23 +455,12 @@ __global__ void __launch_bounds__(kCommThreads) barrier_kernel(const __grid_cons
 }
 
 constexpr size_t kOneshotMaxBytes = 512 * 1024;
-constexpr size_t kPipelineMinBytes = 1 << 20;  // below ~1 MB a single pack/barrier/reduce round is already latency-bound
-// Measured on 2x B200 (profiles/r1_comm_sweep_n2_v3_pipelined.json): the warp-specialised pipeline LOSES to the phase-serial
-// kernel (98.8 vs 65.5 us at 23 MB bf16): with half the threads per role there are half as many peer loads in flight, and
-// the NVLink phase is latency x parallelism bound.  Kept as opt-in algo 3 (bit-exact, tested); not the default.
-constexpr bool kPipelineDefault = false;
-// two-shot all-gather half: pushed by the reducing rank (algo 4) or pulled by the consumers (algo 2)
-constexpr bool kPushDefault = false;
-
-// vectors (all slices together) one CTA moves per pipeline step of algo 5; DMLB_PUSH_STEP_VECTORS overrides it for tuning
-static size_t push_step_vectors() {
-    static size_t value = [] {
-        const char *e = getenv("DMLB_PUSH_STEP_VECTORS");
-        long v = e ? atol(e) : 0;
-        return (size_t)(v >= 8 ? v : 1536);
-    }();
-    return value;
-}
+// NVLS pays off where it removes traffic: per GPU and direction it moves (1 + 1/W) M instead of 2 (W-1)/W M, i.e. nothing at
+// W = 2 and 1.56x less at W = 8; multimem operations also have a longer latency than plain peer loads.  Auto-dispatch uses
+// it from W = 8 and 8 MB upward (profiles/r2_nvls_probe_n{2,4,8}.json); algo = 3 forces it wherever multicast is bound.
+constexpr size_t kNvlsMinBytes = 8 << 20;
+constexpr int kNvlsMinWorld = 8;
+static_assert(sizeof(dmlb_step_metrics) == 1880, "dmlb_step_metrics layout (dmlcloud_b200/_native.py StepMetrics mirrors it)");
 
 }  // namespace dmlb
 
@@ -603,7 +480,9 @@ int dmlb_comm_create(void **comm, int world, int rank, void *const *arenas, size
     c->dev.world = world;
     c->dev.rank = rank;
     c->dev.msg_cap = (max_message_bytes + 255) & ~(size_t)255;
-    c->dev.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    c->dev.timeout_ns = 600ull * 1000 * 1000 * 1000;  // 10 minutes, like NCCL's watchdog default
+    c->dev.mc = nullptr;
+    c->dev.host_err = nullptr;
     for (int r = 0; r < DMLB_MAX_WORLD; ++r) c->dev.arena[r] = r < world ? (unsigned char *)arenas[r] : nullptr;
     for (int r = 0; r < world; ++r)
         if (!c->dev.arena[r] || ((uintptr_t)c->dev.arena[r] & 255)) {
@@ -619,87 +498,83 @@ int dmlb_comm_destroy(void *comm) {
     return DMLB_OK;
 }
 
+int dmlb_comm_configure(void *comm, double timeout_seconds, uint32_t *host_error_word) {
+    if (!comm) return DMLB_EINVAL;
+    Comm *c = reinterpret_cast<Comm *>(comm);
+    if (timeout_seconds > 0.0) c->dev.timeout_ns = (unsigned long long)(timeout_seconds * 1e9);
+    c->dev.host_err = host_error_word;
+    return DMLB_OK;
+}
+
+int dmlb_comm_set_multicast(void *comm, void *mc_base) {
+    if (!comm) return DMLB_EINVAL;
+    reinterpret_cast<Comm *>(comm)->dev.mc = reinterpret_cast<unsigned char *>(mc_base);
+    return DMLB_OK;
+}
+
 int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float scale, double *sumsq, int algo,
-                        void *stream) {
+                        const dmlb_step_metrics *metrics, void *stream) {
     if (!comm || (!bucket && n)) return DMLB_EINVAL;
     if (wire != DMLB_WIRE_F32 && wire != DMLB_WIRE_BF16) return DMLB_EINVAL;
     if ((uintptr_t)bucket & 15) return DMLB_EALIGN;
-    if (n == 0) return DMLB_OK;
+    if (n == 0 && !metrics) return DMLB_OK;
     Comm *c = reinterpret_cast<Comm *>(comm);
+    const int W = c->dev.world;
     const int E = wire == DMLB_WIRE_BF16 ? 8 : 4;
     const size_t nvec = (n + E - 1) / E;
     const size_t bytes = nvec * 16;
-    if (bytes > c->dev.msg_cap) return DMLB_ECAPACITY;
+    if (W > 1 && bytes > c->dev.msg_cap) return DMLB_ECAPACITY;
+    static const dmlb_step_metrics kNoMetrics = {};
+    if (metrics) {
+        const dmlb_step_metrics &m = *metrics;
+        if (!m.acc || !m.cnt || !m.desc || !m.counter || !m.out_ring || m.ring_slots < 1 || m.capacity < 1)
+            return DMLB_EINVAL;
+        if (m.n_folds < 0 || m.n_folds > DMLB_MAX_FOLD_ENTRIES || m.n_ranges < 0 || m.n_ranges > DMLB_MAX_RANGES ||
+            m.n_global_ranges < 0 || m.n_global_ranges > m.n_ranges)
+            return DMLB_ECAPACITY;
+        long long n_glob = 0;
+        for (int j = 0; j < m.n_ranges; ++j) {
+            if (m.ranges[j].begin < 0 || m.ranges[j].end < m.ranges[j].begin || m.ranges[j].end > m.n_cells ||
+                m.ranges[j].end > m.capacity)
+                return DMLB_EINVAL;
+            if (j < m.n_global_ranges) n_glob += m.ranges[j].end - m.ranges[j].begin;
+        }
+        if (n_glob > DMLB_STEP_METRIC_MAX_CELLS) return DMLB_ECAPACITY;
+        for (int j = 0; j < m.n_folds; ++j) {
+            const dmlb_fold_entry &e = m.folds[j];
+            if (e.cell < 0 || e.lanes < 1 || e.k < 0 || e.steps < 1 || e.cell + e.lanes > m.n_cells) return DMLB_EINVAL;
+            if (e.src_dtype == DMLB_SRC_FEED) {
+                if (e.k >= DMLB_FEED_WIDTH || e.lanes != 1) return DMLB_EINVAL;
+            } else if (e.src_dtype < DMLB_F32 || e.src_dtype > DMLB_U8 || e.k < 1) {
+                return DMLB_EINVAL;
+            }
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool pipelined = algo == 3 || (algo == 0 && kPipelineDefault && c->dev.world <= 2 && bytes >= kPipelineMinBytes);
-    if (pipelined) {
-        const int W = c->dev.world;
-        const size_t chunk = 1024;  // wire vectors per chunk per CTA (16 KB)
-        size_t want = (nvec + 4 * chunk - 1) / (4 * chunk);  // ~4 chunks per CTA before spreading wider
-        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
-        if (want > cap) want = cap;
-        const int grid = (int)(want < 1 ? 1 : want);
-        const size_t per = (nvec + grid - 1) / grid;
-        if ((per + chunk - 1) / chunk > 250) return DMLB_ECAPACITY;  // chunk index must fit the flag's low 8 bits
-#define DMLB_LAUNCH_PIPE(WIRE, U) \
-    allreduce_oneshot_pipelined_kernel<WIRE, U><<<grid, 2 * kRole, 0, st>>>(c->dev, bucket, n, nvec, chunk, scale, sumsq)
-        if (wire == DMLB_WIRE_BF16) {
-            if (W <= 2) DMLB_LAUNCH_PIPE(DMLB_WIRE_BF16, 4);
-            else if (W <= 4) DMLB_LAUNCH_PIPE(DMLB_WIRE_BF16, 2);
-            else DMLB_LAUNCH_PIPE(DMLB_WIRE_BF16, 1);
-        } else {
-            if (W <= 2) DMLB_LAUNCH_PIPE(DMLB_WIRE_F32, 4);
-            else if (W <= 4) DMLB_LAUNCH_PIPE(DMLB_WIRE_F32, 2);
-            else DMLB_LAUNCH_PIPE(DMLB_WIRE_F32, 1);
-        }
-#undef DMLB_LAUNCH_PIPE
-        return launched();
-    }
-    if (algo == 5) {
-        const int W = c->dev.world;
-        const size_t S = (nvec + W - 1) / W;
-        if ((size_t)W * S * 16 > c->dev.msg_cap) return DMLB_ECAPACITY;  // the owner's staging half holds W x S vectors
-        size_t chunk = push_step_vectors() / W;  // vectors of ONE slice per pipeline step
-        if (chunk < 1) chunk = 1;
-        size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);
-        size_t want = (S + chunk - 1) / chunk;
-        if (want > cap) want = cap;
-        const int grid = (int)(want < 1 ? 1 : want);
-        const size_t per = (S + grid - 1) / grid;
-        if ((per + chunk - 1) / chunk > 250) chunk = (per + 249) / 250;  // chunk index must fit the flag's low 8 bits
-#define DMLB_LAUNCH_PUSH(WIRE, U) \
-    allreduce_push_pipelined_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, S, chunk, scale, sumsq)
-        if (wire == DMLB_WIRE_BF16) {
-            if (W <= 2) DMLB_LAUNCH_PUSH(DMLB_WIRE_BF16, 4);
-            else if (W <= 4) DMLB_LAUNCH_PUSH(DMLB_WIRE_BF16, 2);
-            else DMLB_LAUNCH_PUSH(DMLB_WIRE_BF16, 1);
-        } else {
-            if (W <= 2) DMLB_LAUNCH_PUSH(DMLB_WIRE_F32, 4);
-            else if (W <= 4) DMLB_LAUNCH_PUSH(DMLB_WIRE_F32, 2);
-            else DMLB_LAUNCH_PUSH(DMLB_WIRE_F32, 1);
-        }
-#undef DMLB_LAUNCH_PUSH
-        return launched();
-    }
-    const bool oneshot = algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || c->dev.world <= 2));
-    const bool push = algo == 4 || (algo == 0 && kPushDefault);
-    const int W = c->dev.world;
+    const bool nvls = W > 1 && c->dev.mc != nullptr &&
+                      (algo == 3 || (algo == 0 && W >= kNvlsMinWorld && bytes >= kNvlsMinBytes));
+    if (algo == 3 && !nvls && W > 1) return DMLB_ESTATE;
+    const bool oneshot = !nvls && (W == 1 || algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || W <= 2)));
     const int kU = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
     const size_t items = oneshot ? nvec : (nvec + W - 1) / W;  // vectors a CTA grid is spread over
     size_t want = (items + (size_t)kCommThreads * kU - 1) / ((size_t)kCommThreads * kU);
-    size_t cap = (size_t)min(kMaxCtas, sm_count() * 2);  // all CTAs co-resident: the per-CTA barriers need that
+    // all CTAs co-resident (the per-CTA barriers need that); one slot is kept for the metric CTA
+    size_t cap = (size_t)min(kMaxCtas, sm_count() * 2) - 1;
     if (want > cap) want = cap;
-    const int grid = (int)(want < 1 ? 1 : want);
-#define DMLB_LAUNCH_AR(WIRE, U)                                                                                       \
-    do {                                                                                                              \
-        if (oneshot)                                                                                                  \
-            allreduce_oneshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq);  \
-        else if (push)                                                                                                \
-            allreduce_twoshot_kernel<WIRE, U, true><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,   \
-                                                                                   scale, sumsq);                     \
-        else                                                                                                          \
-            allreduce_twoshot_kernel<WIRE, U, false><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,  \
-                                                                                    scale, sumsq);                    \
+    const int n_data = n == 0 ? 0 : (int)(want < 1 ? 1 : want);
+    const int grid = n_data + (metrics ? 1 : 0);
+    const dmlb_step_metrics &M = metrics ? *metrics : kNoMetrics;
+#define DMLB_LAUNCH_AR(WIRE, U)                                                                                          \
+    do {                                                                                                                 \
+        if (oneshot)                                                                                                     \
+            allreduce_oneshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq,      \
+                                                                             n_data, M);                                 \
+        else if (nvls)                                                                                                   \
+            allreduce_twoshot_kernel<WIRE, U, true><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,       \
+                                                                                   scale, sumsq, n_data, M);             \
+        else                                                                                                             \
+            allreduce_twoshot_kernel<WIRE, U, false><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,      \
+                                                                                    scale, sumsq, n_data, M);            \
     } while (0)
     if (wire == DMLB_WIRE_BF16) {
         if (kU == 4) DMLB_LAUNCH_AR(DMLB_WIRE_BF16, 4);
@@ -718,7 +593,7 @@ int dmlb_comm_error(void *comm, int *error) {
     if (!comm || !error) return DMLB_EINVAL;
     Comm *c = reinterpret_cast<Comm *>(comm);
     uint32_t word = 0;
-    // the error word lives in this rank's own arena (control block, word 2); a blocking 4-byte read: call it per epoch
+    // the error word lives in this rank's own arena (control block, word 2); a blocking 4-byte read
     DMLB_CUDA(cudaMemcpy(&word, c->dev.arena[c->dev.rank] + 2 * sizeof(uint32_t), sizeof(word), cudaMemcpyDeviceToHost));
     *error = (int)word;
     return DMLB_OK;

@@ -141,6 +141,137 @@ class _PendingResult:
         return self._parsed
 
 
+class StepRing:
+    """Results of the fused step exchange: `SLOTS` result blocks (layout of DeviceSlab.out) in device-mapped pinned host
+    memory.  Exchange number k (1-based) writes slot (k-1) % SLOTS and stamps it with k last, so the host needs neither a
+    copy nor an event: it reads the slot once its stamp says k."""
+
+    SLOTS = 8
+
+    def __init__(self, lib, capacity):
+        self.capacity = capacity
+        self.slot_bytes = STATUS_BYTES + 9 * capacity
+        self.host = torch.zeros(self.SLOTS, self.slot_bytes, dtype=torch.uint8).pin_memory()
+        out = ctypes.c_void_p()
+        N.check(lib.dmlb_host_device_pointer(self.host.data_ptr(), ctypes.byref(out)), 'host_device_pointer(ring)')
+        self.device_ptr = out.value
+        self._stamps = self.host.numpy()[:, STATUS_BYTES - 8:STATUS_BYTES].view('<u8').reshape(self.SLOTS)
+
+    def stamp(self, k):
+        return int(self._stamps[(k - 1) % self.SLOTS])
+
+    def latest(self):
+        return int(self._stamps.max())
+
+    def wait(self, k, sync=None, spin_seconds=30.0):
+        """Block until exchange k has landed (or a later one has overwritten its slot: returns that newer number)."""
+        import time
+
+        got = self.stamp(k)
+        if got >= k:
+            return got
+        deadline = time.perf_counter() + spin_seconds
+        while True:
+            got = self.stamp(k)
+            if got >= k:
+                return got
+            if time.perf_counter() > deadline:
+                if sync is not None:
+                    sync()
+                    got = self.stamp(k)
+                    if got >= k:
+                        return got
+                raise RuntimeError(f'step exchange {k} never reported its results (stamp {got})')
+
+    def read(self, k):
+        row = self.host[(k - 1) % self.SLOTS]
+        cap = self.capacity
+        status = int(row[:4].view(torch.int32)[0])
+        vals = row[STATUS_BYTES:STATUS_BYTES + 8 * cap].view(torch.int64).clone()
+        flags = row[STATUS_BYTES + 8 * cap:STATUS_BYTES + 9 * cap].clone()
+        return status, vals, flags
+
+
+class _RingResult:
+    """_PendingResult face over one exchange of a StepRing."""
+
+    def __init__(self, ring, k, sync=None):
+        self.ring, self.k, self.sync = ring, k, sync
+        self._parsed = None
+
+    def ready(self):
+        return self._parsed is not None or self.ring.stamp(self.k) >= self.k
+
+    def get(self):
+        if self._parsed is None:
+            self.ring.wait(self.k, self.sync)
+            self._parsed = self.ring.read(self.k)
+        return self._parsed
+
+
+def _raise_for_status(status):
+    if status == N.METRIC_TIMEOUT:
+        raise RuntimeError('a peer did not arrive at the metric exchange barrier in time: a rank died or the ranks '
+                           'issued different collectives; the reduced metrics of this exchange are invalid')
+    if status != N.METRIC_OK:
+        raise ValueError(SPLIT_VOTE_MSG)
+
+
+class HostFeed:
+    """Host scalars on their way INTO a captured step (graphstep.GraphedTrainStep): a ring of slots in device-mapped
+    pinned host memory, one slot per graph replay, read by the metric CTA of the fused step exchange (fold entries with
+    src_dtype == DMLB_SRC_FEED).  Column j carries the pre-combined python scalars tracked for one slab cell since the
+    previous replay (e.g. misc/step_time_ms, reference stage.py:314) and how many they were."""
+
+    SLOTS = 64
+
+    def __init__(self, lib):
+        self.cols, self.kind = {}, {}
+        self.host = torch.zeros(self.SLOTS, 2 * N.FEED_WIDTH, dtype=torch.float64).pin_memory()
+        out = ctypes.c_void_p()
+        N.check(lib.dmlb_host_device_pointer(self.host.data_ptr(), ctypes.byref(out)), 'host_device_pointer(feed)')
+        self.device_ptr = out.value
+        self.rows = self.host.numpy()
+        self.pending = {}  # cell -> [value, count]
+
+    def assign(self, cells):
+        """cells: {cell: (op code, is_int)} — at most FEED_WIDTH of them; column j carries the j-th cell."""
+        if len(cells) > N.FEED_WIDTH:
+            raise ValueError(f'at most {N.FEED_WIDTH} host-scalar metrics can be fed into a captured step')
+        self.cols = {cell: j for j, cell in enumerate(sorted(cells))}
+        self.kind = {cell: cells[cell] for cell in self.cols}
+
+    def put(self, cell, value):
+        slot = self.pending.get(cell)
+        if slot is None:
+            self.pending[cell] = [value, 1]
+            return
+        op, is_int = self.kind[cell]
+        if op == N.MIN:
+            slot[0] = min(slot[0], value)
+        elif op == N.MAX:
+            slot[0] = max(slot[0], value)
+        else:
+            slot[0] += value
+        slot[1] += 1
+
+    def commit(self, replay_index):
+        """Write what was put since the last commit into the slot replay number `replay_index` (0-based) will read."""
+        row = self.rows[replay_index % self.SLOTS]
+        row[N.FEED_WIDTH:] = 0.0
+        for cell, (value, count) in self.pending.items():
+            j = self.cols[cell]
+            row[j] = value
+            row[N.FEED_WIDTH + j] = count
+        self.pending = {}
+
+    def drain(self):
+        """[(cell, combined value, count)] not yet handed to a replay (epoch end)."""
+        out = [(cell, v, n) for cell, (v, n) in self.pending.items()]
+        self.pending = {}
+        return out
+
+
 class DeviceSlab:
     """HBM layout: acc u64[C] | cnt i64[C] | desc u32[C]  +  out = status(32 x i32) | val u64[C] | flag u8[C].
     Results destined for the host are written by the reduce kernel directly into device-mapped pinned host memory
@@ -172,8 +303,14 @@ class DeviceSlab:
         self._host_dptr = {}
         self._range_cache = {}
         self._host_mapped = None  # None = not probed yet; False = pinned memory is not device-mapped here (copy path)
-        self._imm = []
-        self._imm_cells = set()
+        self._imm = []           # queued fold entries (immediates, and device values while batching)
+        self._imm_cells = set()  # cells the queue touches (an entry per cell per launch: folds are not atomic)
+        self._imm_index = {}     # cell -> position of its queued immediate (python scalars of one cell are pre-combined)
+        self._keep = []          # tensors the queued device entries read
+        self.batching = False    # True: device values are queued too and ride in ONE launch per step (stage.py)
+        self.feed = None         # HostFeed of a captured step: python scalars of its cells go there instead of a launch
+        self.imm_cells_seen = {}  # cell -> (op, is_int) of every cell that ever received a python scalar
+        self.generation = 0      # bumped when the buffers are reallocated (captured graphs hold raw pointers)
         self._grow(self.GROW)
 
     # -- memory ------------------------------------------------------------------------------------------------------
@@ -191,6 +328,7 @@ class DeviceSlab:
         self.capacity = capacity
         self._ptrs = (self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), self.out.data_ptr())
         self._host_pool = []
+        self.generation += 1
 
     def _lib(self):
         return N.cuda_lib(self.device.index)
@@ -207,7 +345,7 @@ class DeviceSlab:
         return c0
 
     def reset_cells(self, cell, lanes):
-        self.flush()
+        self.flush_all()
         N.check(self._lib().dmlb_metric_reset(self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), cell,
                                               cell + lanes, N.stream_ptr()), 'metric_reset')
 
@@ -246,11 +384,27 @@ class DeviceSlab:
         return self._event_pool.pop() if self._event_pool else torch.cuda.Event()
 
     # -- fold --------------------------------------------------------------------------------------------------------
-    def fold_imm(self, cell, value, is_int):
-        """Queue a host scalar; it rides along with the next launch (or the reduce)."""
-        if cell in self._imm_cells or len(self._imm) >= N.MAX_FOLD_ENTRIES - 1:
+    def fold_imm(self, cell, value, is_int, op=N.SUM):
+        """Queue a host scalar; it rides along with the next launch (or the reduce).  Scalars for the same cell are
+        combined on the host (fp64 / int, the cell's own arithmetic), so a per-step python value never costs a launch."""
+        self.imm_cells_seen[cell] = (op, is_int)
+        value = int(value) if is_int else float(value)
+        feed = self.feed
+        if feed is not None and cell in feed.cols:
+            feed.put(cell, value)
+            return
+        at = self._imm_index.get(cell)
+        if at is not None:
+            e = self._imm[at]
+            old = e.imm if is_int else struct.unpack('<d', struct.pack('<q', e.imm))[0]
+            new = min(old, value) if op == N.MIN else (max(old, value) if op == N.MAX else old + value)
+            e.imm = new if is_int else struct.unpack('<q', struct.pack('<d', new))[0]
+            e.steps += 1
+            return
+        if cell in self._imm_cells or len(self._imm) >= N.MAX_FOLD_ENTRIES:
             self.flush()
-        bits = int(value) if is_int else struct.unpack('<q', struct.pack('<d', float(value)))[0]
+        bits = value if is_int else struct.unpack('<q', struct.pack('<d', value))[0]
+        self._imm_index[cell] = len(self._imm)
         self._imm.append(N.FoldEntry(None, bits, N.F64, cell, 1, 1, 1, 0))
         self._imm_cells.add(cell)
 
@@ -260,17 +414,40 @@ class DeviceSlab:
         if code is None:
             tensor = tensor.to(torch.float64 if tensor.dtype.is_floating_point else torch.int64)
             code = _SRC_CODE[tensor.dtype]
-        if any(cell <= c < cell + lanes for c in self._imm_cells):
+        if len(self._imm) >= N.MAX_FOLD_ENTRIES or any(cell <= c < cell + lanes for c in self._imm_cells):
             self.flush()
-        entries = self._imm + [N.FoldEntry(tensor.data_ptr(), 0, code, cell, lanes, k, steps, 0)]
-        self._imm, self._imm_cells = [], set()
-        self._launch_fold(entries)
+        self._imm.append(N.FoldEntry(tensor.data_ptr(), 0, code, cell, lanes, k, steps, 0))
+        self._imm_cells.update(range(cell, cell + lanes))
+        self._keep.append(tensor)  # the queued entry reads it: keep the storage alive until the launch
+        if not self.batching:
+            self.flush()
         return tensor  # caller keeps it alive until the stream passes (torch's allocator is stream-ordered)
 
+    def take_batch(self):
+        """The queued fold entries, NOT launched: the fused step exchange folds them itself (graphstep.py)."""
+        entries, keep = self._imm, self._keep
+        self._imm, self._imm_cells, self._imm_index, self._keep = [], set(), {}, []
+        return entries, keep
+
     def flush(self):
+        """Launch what is queued (one launch).  Scalars waiting in a captured step's feed ring stay there: the next
+        replay picks them up."""
         if self._imm:
-            entries, self._imm, self._imm_cells = self._imm, [], set()
+            entries, _ = self.take_batch()
             self._launch_fold(entries)
+
+    def flush_all(self):
+        """flush() + the feed ring's leftovers as immediates: everything tracked so far is in the cells afterwards
+        (reduce / reset / export / end of a stage)."""
+        if self.feed is not None:
+            for cell, value, count in self.feed.drain():
+                op, is_int = self.feed.kind[cell]
+                bits = value if is_int else struct.unpack('<q', struct.pack('<d', value))[0]
+                if cell in self._imm_cells or len(self._imm) >= N.MAX_FOLD_ENTRIES:
+                    self.flush()
+                self._imm.append(N.FoldEntry(None, bits, N.F64, cell, 1, 1, count, 0))
+                self._imm_cells.add(cell)
+        self.flush()
 
     def _launch_fold(self, entries):
         arr = (N.FoldEntry * len(entries))(*entries)
@@ -294,8 +471,7 @@ class DeviceSlab:
         if hit is None:
             if len(self._range_cache) > 64:
                 self._range_cache.clear()
-            chunks = [key[i:i + N.MAX_RANGES] for i in range(0, len(key), N.MAX_RANGES)] or [()]
-            hit = [((N.Range * max(len(c), 1))(*[N.Range(b, e) for b, e in c]), len(c)) for c in chunks]
+            hit = ((N.Range * max(len(key), 1))(*[N.Range(b, e) for b, e in key]), len(key))
             self._range_cache[key] = hit
         return hit
 
@@ -303,7 +479,7 @@ class DeviceSlab:
         """Finalise + cross-rank combine.  `global_ranges` are the cells of globally-reduced metrics (identical layout
         on every rank, covered by `layout_hash`, exchanged); `local_ranges` are rank-local metrics (never exchanged,
         may differ between ranks).  Returns a _PendingResult (to_host) or None."""
-        self.flush()
+        self.flush_all()
         lib = self._lib()
         world, rank = self._world_rank()
         if not exchange:
@@ -320,24 +496,35 @@ class DeviceSlab:
         if base == out_p:  # device-resident block: clear the sticky status slots (pooled host blocks are handed out zeroed)
             N.check(lib.dmlb_memset_async(status_ptr, 0, STATUS_BYTES, st), 'memset(status)')
 
-        def launch(comm_handle, ranges):
-            # > DMLB_MAX_RANGES fragments (pathological prefix selections) take several launches
-            for arr, n in self._range_array(ranges):
-                if n == 0 and comm_handle is None:
-                    continue
-                rc = lib.dmlb_metric_reduce(comm_handle, acc_p, cnt_p, desc_p, self.n_cells, arr, n, layout_hash,
-                                            int(reset), val_ptr, flag_ptr, status_ptr, st)
-                if rc:
-                    N.check(rc, 'metric_reduce')
+        def launch(comm_handle, glob, loc):
+            # the exchanged (global) ranges must fit ONE launch: every rank has to issue the same number of collectives
+            if len(glob) > N.MAX_RANGES:
+                raise RuntimeError(f'the globally-reduced metric selection is fragmented into {len(glob)} cell ranges '
+                                   f'(max {N.MAX_RANGES} per exchange)')
+            room = N.MAX_RANGES - len(glob)
+            first = True
+            rest = list(loc)
+            while first or rest:
+                part, rest = rest[:room], rest[room:]
+                g = glob if first else []
+                arr, n = self._range_array(tuple(g) + tuple(part))
+                handle = comm_handle if first else None  # rank-local leftovers never touch the communicator
+                if n or handle is not None:
+                    rc = lib.dmlb_metric_reduce(handle, acc_p, cnt_p, desc_p, self.n_cells, arr, n, len(g), layout_hash,
+                                                int(reset), val_ptr, flag_ptr, status_ptr, st)
+                    if rc:
+                        N.check(rc, 'metric_reduce')
+                first = False
+                room = N.MAX_RANGES
 
         if world == 1:
-            launch(None, list(global_ranges) + list(local_ranges))
+            launch(None, [], list(global_ranges) + list(local_ranges))
         elif self.comm is not None:
-            # fused path: global cells first (their record index must agree across ranks), rank-local cells after
-            launch(self.comm.handle, list(global_ranges) + list(local_ranges))
+            # fused path: global cells are exchanged (their record index must agree across ranks), rank-local cells are not
+            launch(self.comm.handle, list(global_ranges), list(local_ranges))
         else:
             if local_ranges:
-                launch(None, list(local_ranges))
+                launch(None, [], list(local_ranges))
             self._reduce_via_collective(lib, list(global_ranges), layout_hash, reset, world, rank, val_ptr, flag_ptr,
                                         status_ptr, st)
         if not to_host:
@@ -385,7 +572,7 @@ class DeviceSlab:
 
     # -- checkpoint --------------------------------------------------------------------------------------------------
     def export_cells(self, cell, lanes):
-        self.flush()
+        self.flush_all()
         return self.acc[cell:cell + lanes].cpu(), self.cnt[cell:cell + lanes].cpu()
 
     def import_cells(self, cell, acc, cnt):
@@ -556,8 +743,7 @@ class MetricReducer:
         if any(v != ('values',) for v in votes):
             raise ValueError(SPLIT_VOTE_MSG)
         result, status = _device_reduce(stacked, self.reduction, dims, steps_axis=True, group=group, globally=True)
-        if int(status[0]) != N.METRIC_OK:
-            raise ValueError(SPLIT_VOTE_MSG)
+        _raise_for_status(int(status[0]))
         return result
 
     def state_dict(self):
@@ -648,7 +834,7 @@ class SlabMetric:
             raise RuntimeError(f'stack expects each tensor to be equal size, but got {self.value_shape} and {shape} '
                                f'for metric {self.name}')
         if scalar is not None:
-            slab.fold_imm(self.cell, scalar, self.is_int)
+            slab.fold_imm(self.cell, scalar, self.is_int, self.reduction.code)
         else:
             if not value.is_cuda:
                 value = value.to(slab.device)
@@ -771,8 +957,7 @@ class MetricTracker:
         if metric.lanes != 1 or len(metric.residual_shape) != 0:
             return cls._decode(pending, metric)
         status, vals, flags = pending.get()
-        if status != N.METRIC_OK:
-            raise ValueError(SPLIT_VOTE_MSG)
+        _raise_for_status(status)
         per = bulk.get(id(pending))
         if per is None:
             per = bulk[id(pending)] = {'flags': flags.tolist()}
@@ -788,8 +973,7 @@ class MetricTracker:
     @staticmethod
     def _decode(pending, metric):
         status, vals, flags = pending.get()
-        if status != N.METRIC_OK:
-            raise ValueError(SPLIT_VOTE_MSG)
+        _raise_for_status(status)
         if isinstance(metric, _VoteOnly):
             return None
         c0, lanes = metric.cell, metric.lanes
@@ -934,16 +1118,26 @@ class MetricTracker:
         the per-step metric exchange of BASELINE configs 2/3.  Returns a mapping {name: handle}; `handle.value()`
         brings the number to the host (one event sync) when it is actually needed.  The selection (cell ranges, layout
         hash) is cached while the metric set is unchanged, so the per-step host cost does not grow with #metrics."""
+        by_name, plan = self.live_selection(prefix)
+        if not by_name:
+            return {}
+        pending = self._launch(None, reset=False, plan=plan)
+        return _LiveView(pending, by_name)
+
+    def live_selection(self, prefix=None):
+        """({name: metric}, (global ranges, local ranges, layout hash)) of the running metrics a live exchange covers:
+        every reduced metric that owns cells and has no value for this epoch yet.  Cached while the metric set is
+        unchanged, so the per-step host cost does not grow with #metrics."""
         key = (self._version, prefix, self.epoch)
         if self._live_plan is None or self._live_plan[0] != key:
             metrics = [m for name, m in self.reducers.items()
                        if (prefix is None or name.startswith(prefix)) and m.cell is not None
                        and not self.has_value(name)]
             self._live_plan = (key, {m.name: m for m in metrics}, self._plan(metrics) if metrics else None)
-        _, by_name, plan = self._live_plan
-        if not by_name:
-            return {}
-        pending = self._launch(None, reset=False, plan=plan)
+        return self._live_plan[1], self._live_plan[2]
+
+    def live_view(self, pending, by_name):
+        """Mapping name -> handle over an exchange somebody else launched (the fused step exchange of a captured step)."""
         return _LiveView(pending, by_name)
 
     def next_epoch(self):

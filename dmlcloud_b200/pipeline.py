@@ -304,10 +304,19 @@ class TrainingPipeline:
     def _pre_epoch(self):
         pass
 
+    def _comms(self):
+        return [c for c in [self.metric_comm] + [s.comm for s in self.grad_syncs.values()] if c is not None]
+
+    def poll_comm_errors(self):
+        """Raise if a libdmlb collective gave up waiting for a peer.  The kernels report through a word in mapped pinned
+        host memory, so this is two plain memory reads — the stage calls it every step."""
+        for comm in self._comms():
+            if comm.failed():
+                comm.check()
+
     def _post_epoch(self):
-        for comm in [self.metric_comm] + [s.comm for s in self.grad_syncs.values()]:
-            if comm is not None:
-                comm.check()  # a timed-out peer barrier surfaces here, once per epoch
+        for comm in self._comms():
+            comm.check(blocking=True)  # (also reads the device-side error word, in case the host word is unavailable)
         if self.wandb and is_root():
             import wandb
 

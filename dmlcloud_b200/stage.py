@@ -10,8 +10,9 @@ for the reference run unchanged.  What happens underneath a step is different:
       and all-reduces it over gloo / NCCL                  K1 -> fused NVLink peer all-reduce (or NCCL) -> K2
   4x track_reduce: D2H copy + stream sync per CUDA       values fold into the device-resident metric slab; python
       value, python list append (metrics.py:72,234)        scalars travel as kernel immediates; no sync in the loop
-  clip_grad_norm_ per param group (host reads norm)      fused sum-of-squares + clip kernels, coefficient stays on GPU
-  metrics cross ranks once per epoch                      optionally every N steps too (`live_metrics_every`), same kernel
+  clip_grad_norm_ per param group (host reads norm)      sum of squares fused into the all-reduce, coefficient stays on GPU
+  metrics cross ranks once per epoch                      optionally every N steps too (`live_metrics_every`); in a captured
+                                                            step the exchange rides inside the gradient all-reduce kernel
 
 Fixed quirks: only rank 0 prints the table (the reference tests the function object `is_root`, always
 true); the ETA cell is skipped when max_epochs is None instead of raising.
@@ -115,6 +116,9 @@ class Stage:
         self.pipeline.barrier(self.barrier_timeout)
 
     def _post_stage(self):
+        graph = getattr(self, '_graph', None)
+        if graph is not None:
+            graph.detach()
         self.table.close()
         self.post_stage()
         self.pipeline.barrier(self.barrier_timeout)
@@ -216,16 +220,37 @@ class TrainValStage(Stage):
             opt.zero_grad()
 
     def clip_gradients(self):
+        """clip_grad_norm_ per optimizer param group (reference stage.py:276-279).  When one param group holds exactly the
+        parameters of the one DDP model, the sum of squares the gradient all-reduce accumulated while it wrote the reduced
+        buckets IS that group's squared norm: clipping then costs one scale pass and no extra read of the gradients."""
         from .gradsync import clip_grad_norm_
 
         limit = self.gradient_clip()
-        for opt in self.optimizers():
-            for group in opt.param_groups:
-                clip_grad_norm_(group['params'], limit)
+        groups = [g for opt in self.optimizers() for g in opt.param_groups]
+        fused = self._fused_sumsq(groups)
+        for group in groups:
+            clip_grad_norm_(group['params'], limit, sumsq=fused)
+
+    def _fused_sumsq(self, groups):
+        syncs = list(self.pipeline.grad_syncs.items())
+        if len(groups) != 1 or len(syncs) != 1:
+            return None
+        name, sync = syncs[0]
+        if sync.sumsq is None or sync.buckets_this_step == 0:
+            return None
+        model = self.pipeline.models[name]
+        wanted = {id(p) for p in model.parameters() if p.requires_grad}
+        if {id(p) for p in groups[0]['params'] if p.grad is not None} != wanted:
+            return None
+        torch.cuda.current_stream(self.device).wait_stream(sync.comm_stream)  # (DDP's finalize already waited; cheap)
+        return sync.sumsq
 
     def optimize(self, loss):
+        clip = bool(self.gradient_clip())
+        for sync in self.pipeline.grad_syncs.values():
+            sync.begin_step(track_sumsq=clip)
         loss.backward()  # -> DDP Reducer -> GradBucketSync.hook per bucket (libdmlb kernels on the comm stream)
-        if self.gradient_clip():
+        if clip:
             self.clip_gradients()
         for opt in self.optimizers():
             opt.step()
@@ -263,23 +288,30 @@ class TrainValStage(Stage):
         if hasattr(sampler, 'set_epoch'):
             sampler.set_epoch(self.current_epoch)
 
+        slab = self.tracker._slab_or_create()
         for batch in loader:
             began = time.perf_counter_ns()
-            in_graph = self._graphed_step(batch) if self.cuda_graph else False
-            if not in_graph:
-                self.zero_grad()
-                loss = self.train_step(batch)
-                self.optimize(loss)
-            step_ms = (time.perf_counter_ns() - began) / 1e6  # host time, like the reference (not device-synchronised)
+            slab.batching = True  # everything this step tracks rides in ONE fold launch (none at all in a captured step)
+            try:
+                in_graph = self._graphed_step(batch) if self.cuda_graph else False
+                if not in_graph:
+                    self.zero_grad()
+                    loss = self.train_step(batch)
+                    self.optimize(loss)
+                step_ms = (time.perf_counter_ns() - began) / 1e6  # host time, like the reference (not device-synchronised)
 
-            if not in_graph:  # (the captured step folds its loss and batch counters itself)
-                self.track_reduce(self.loss_metric_name(), loss)
-                self._count_batch('train')
-            self.track_reduce('misc/step_time_ms', step_ms, prefixed=False)
+                if not in_graph:  # (the captured step folds its loss and batch counters itself)
+                    self.track_reduce(self.loss_metric_name(), loss)
+                    self._count_batch('train')
+                self.track_reduce('misc/step_time_ms', step_ms, prefixed=False)
+            finally:
+                slab.batching = False
+            slab.flush()
 
             self.global_step += 1
-            if self.live_metrics_every and self.global_step % self.live_metrics_every == 0:
-                self.live_metrics = self.tracker.reduce_live()
+            if not in_graph and self.live_metrics_every and self.global_step % self.live_metrics_every == 0:
+                self.live_metrics = self.tracker.reduce_live()  # (a captured step exchanges inside its own kernel)
+            self.pipeline.poll_comm_errors()  # a dead peer stops the run at this step, not at the end of the epoch
 
         for name, scheduler in self.pipeline.schedulers.items():
             self.track(f'misc/lr_{name}', scheduler.get_last_lr()[0], prefixed=False)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMLB_ABI_VERSION 1
+#define DMLB_ABI_VERSION 2
 
 #define DMLB_OK 0
 #define DMLB_EINVAL (-10001)   /* bad argument (null pointer, n out of range, unknown enum)              */
@@ -122,9 +122,20 @@ typedef struct {
     uint32_t done; /* internal: CTAs that have finished the current launch */
     uint32_t _pad;
 } dmlb_adam_state;
+/* lr_dev (optional): DEVICE double holding the learning rate; when non-NULL it overrides `lr`, so a CUDA graph that
+ * captured this launch follows a scheduler (reference stage.py:316-318 `scheduler.step()`) without re-capture. */
 int dmlb_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n, double lr,
                        double beta1, double beta2, double eps, double weight_decay, int decoupled, int maximize,
-                       const double *sumsq, float max_norm, dmlb_adam_state *state, int advance, void *stream);
+                       const double *sumsq, float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev,
+                       void *stream);
+/* K6: torch.optim.SGD step on flat fp32 buffers (ResNet-18 config: SGD + momentum), 16-20 B/elem:
+ *   g = coef * grad (clip coefficient as in K5; negated for maximize);  g += wd * p;
+ *   momentum != 0:  buf = first ? g : momentum * buf + (1 - dampening) * g;   g = nesterov ? g + momentum * buf : buf
+ *   p -= lr * g.     `first` = state->step == 0 (torch initialises the momentum buffer with the first gradient).
+ * momentum_buf may be NULL when momentum == 0.  state / advance / lr_dev as for K5. */
+int dmlb_sgd_step_f32(float *param, const float *grad, float *momentum_buf, size_t n, double lr, double momentum,
+                      double dampening, double weight_decay, int nesterov, int maximize, const double *sumsq,
+                      float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev, void *stream);
 
 /* Multi-tensor variants: gather `count` parameter gradients straight into / out of one flat wire buffer (the graph-
  * captured step keeps no DDP Reducer).  `segs` is a DEVICE array of dmlb_seg built once at registration. */
@@ -157,18 +168,60 @@ size_t dmlb_comm_arena_bytes(size_t max_message_bytes);
 /* `arenas[r]` is rank r's arena mapped into THIS process (own pointer at index `rank`); all zero-filled before use. */
 int dmlb_comm_create(void **comm, int world, int rank, void *const *arenas, size_t max_message_bytes);
 int dmlb_comm_destroy(void *comm);
+/* Dead-peer handling.  timeout_seconds: how long a flag barrier waits for a peer (default 600 s, like NCCL's watchdog;
+ * <= 0 keeps the current value).  host_error_word: DEVICE address of a uint32 in device-mapped pinned host memory (or
+ * NULL): set to 1 by the kernel that timed out, so the host can poll it every step without a synchronisation.  A
+ * collective that timed out POISONS its outputs (NaN gradients / DMLB_METRIC_TIMEOUT) instead of writing partial sums. */
+int dmlb_comm_configure(void *comm, double timeout_seconds, uint32_t *host_error_word);
+/* Attach the NVSwitch multicast mapping of the arenas (dmlb_vmm_* below): enables algo 3. */
+int dmlb_comm_set_multicast(void *comm, void *mc_base);
+
+/* The per-step metric exchange that rides along with the gradient all-reduce (fused step exchange).  One extra CTA of the
+ * all-reduce kernel: folds this step's tracked values into the slab, finalises the selected cells WITHOUT resetting them
+ * (the running value of the epoch so far), exchanges 16-byte records through the arena's metric staging area under the
+ * SAME flag barrier as the gradients, combines in rank order and writes the results into slot (count % ring_slots) of
+ * `out_ring` — normally device-mapped pinned host memory, so the host reads them with no copy and no launch.
+ * Replaces reference stage.py:305-314 (4x track_reduce per step) + metrics.py:121-141 at per-step granularity.
+ *   slot layout: int32 status[DMLB_METRIC_STATUS_SLOTS] (slot 0 used; bytes 120..127 = uint64 stamp = count + 1,
+ *                written last) | uint64 val[capacity] | uint8 flag[capacity]
+ *   ranges: global cell ranges first (n_global_ranges of them; layout identical on all ranks, covered by layout_hash),
+ *           rank-local ranges after; at most DMLB_STEP_METRIC_MAX_CELLS global cells.
+ *   feed:   device address of a mapped pinned host ring [feed_slots][2 * DMLB_FEED_WIDTH] doubles (values, counts) for
+ *           host scalars (e.g. misc/step_time_ms); fold entries with src_dtype == DMLB_SRC_FEED and k = column read slot
+ *           (count % feed_slots); their `src` field is ignored.  NULL / 0 when unused.
+ *   counter: device uint64, number of exchanges done through this descriptor (the kernel increments it). */
+typedef struct dmlb_step_metrics dmlb_step_metrics; /* defined below, after the metric slab types */
+
 /* in-place averaged all-reduce of an fp32 bucket: bucket = sum_r wire(bucket_r * scale)  (scale = 1/W).
- * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot (reduced slices pulled by the peers),
- * 3 one-shot tile-pipelined (pack warps and reduce warps of a CTA work on different chunks at the same time; per-chunk
- * flags), 4 two-shot with the reduced slices pushed into every peer's arena by the rank that reduced them, 5 two-shot
- * push-pipelined (scatter and gather both as posted peer stores, chunked, control warps do the signalling). */
+ * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot (reduce-scatter + all-gather through
+ * peer loads), 3 NVLS (in-switch reduction: multimem.ld_reduce of this rank's slice + multimem.st of the sum; needs
+ * dmlb_comm_set_multicast; the switch's summation order replaces the rank order, see DESIGN.md numerics).
+ * metrics (optional, host struct copied by value): the fused step exchange above.  n may be 0 with metrics != NULL
+ * (metric-only step).  With world == 1 the same kernel runs without staging or barrier (bucket rounded through the wire
+ * dtype in place), so numerics and launch structure do not depend on W. */
 int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float scale, double *sumsq, int algo,
-                        void *stream);
+                        const dmlb_step_metrics *metrics, void *stream);
 /* one flag barrier across all ranks on `stream` (setup / tests) */
 int dmlb_comm_barrier(void *comm, void *stream);
-/* *error != 0 after a peer failed to arrive at a barrier within 10 s (the kernels then fall through instead of hanging
- * the GPU; results of that collective are garbage).  Blocking 4-byte device read: poll it per epoch, not per step. */
+/* *error != 0 after a peer failed to arrive at a barrier within the timeout.  Blocking 4-byte device read; the host
+ * normally polls the mapped word of dmlb_comm_configure instead. */
 int dmlb_comm_error(void *comm, int *error);
+
+/* Shareable device memory for NVSwitch multicast (driver VMM API reached through cudaGetDriverEntryPoint; no link-time
+ * dependency on libcuda).  A rank allocates its arena with dmlb_vmm_alloc (POSIX file descriptor in *fd: pass it to the
+ * peers over a unix socket), maps the peers' arenas with dmlb_vmm_import, and all ranks bind their arena to ONE multicast
+ * object (rank 0: dmlb_mc_create -> fd to the peers; everyone: dmlb_mc_bind).  Sizes are rounded up to the multicast
+ * granularity, returned by dmlb_vmm_granularity (0 = multicast unsupported on this device). */
+size_t dmlb_vmm_granularity(int device, int world);
+int dmlb_vmm_alloc(int device, size_t bytes, void **ptr, int *fd, uint64_t *handle);
+int dmlb_vmm_import(int device, int fd, size_t bytes, void **ptr, uint64_t *handle);
+int dmlb_vmm_free(void *ptr, size_t bytes, uint64_t handle);
+int dmlb_mc_create(int world, size_t bytes, int *fd, uint64_t *mc_handle);
+int dmlb_mc_import(int fd, uint64_t *mc_handle);
+int dmlb_mc_add_device(uint64_t mc_handle, int device);
+/* bind this rank's arena (its allocation handle) to the multicast object and map the object: *mc_ptr = multicast VA */
+int dmlb_mc_bind(uint64_t mc_handle, int device, uint64_t mem_handle, size_t bytes, void **mc_ptr);
+int dmlb_mc_release(uint64_t mc_handle, void *mc_ptr, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* K3 / K4 — device-resident metric slab                                                                              */
@@ -193,7 +246,8 @@ typedef struct {
     int32_t cell;      /* first cell of the metric                                                                */
     int32_t lanes;     /* number of cells (un-reduced elements)                                                   */
     int32_t k;         /* contiguous elements folded into each cell per step                                      */
-    int32_t steps;     /* >= 1: src is [steps, lanes, k] (a stack of step values, MetricReducer.reduce_locally)    */
+    int32_t steps;     /* >= 1: src is [steps, lanes, k] (a stack of step values, MetricReducer.reduce_locally);   *
+                        * for an immediate: how many host scalars `imm` already combines (cnt += steps)            */
     int32_t _pad;
 } dmlb_fold_entry;
 #define DMLB_MAX_FOLD_ENTRIES 32
@@ -208,6 +262,26 @@ typedef struct {
     int32_t begin, end; /* cell range [begin, end) selected for this reduce */
 } dmlb_range;
 #define DMLB_MAX_RANGES 64
+
+/* descriptor of the fused step exchange (see dmlb_comm_allreduce above) */
+#define DMLB_FEED_WIDTH 16
+#define DMLB_SRC_FEED 7
+#define DMLB_STEP_METRIC_MAX_CELLS 1023
+struct dmlb_step_metrics {
+    uint64_t *acc;
+    int64_t *cnt;
+    const uint32_t *desc;
+    uint64_t *counter;
+    unsigned char *out_ring;
+    const double *feed;
+    uint64_t layout_hash;
+    int32_t n_cells, capacity;
+    int32_t ring_slots, feed_slots;
+    int32_t n_folds, n_ranges, n_global_ranges, _pad;
+    dmlb_fold_entry folds[DMLB_MAX_FOLD_ENTRIES];
+    dmlb_range ranges[DMLB_MAX_RANGES];
+};
+
 /* status: DMLB_METRIC_STATUS_SLOTS int32 slots; every CTA of a reduce / combine launch raises its own slot (slot i < grid) to
  * the worst condition it saw (sticky: max with the slot's content, no atomics).  The caller zero-fills the block before a
  * reduce (which may take several launches) and takes the maximum over the slots afterwards. */
@@ -215,17 +289,22 @@ typedef struct {
 #define DMLB_METRIC_OK 0
 #define DMLB_METRIC_SPLIT_VOTE 1 /* some ranks tracked values and some did not (metrics.py:127-128) */
 #define DMLB_METRIC_LAYOUT 2     /* ranks disagree on the slab layout                                */
+#define DMLB_METRIC_TIMEOUT 3    /* a peer did not arrive at the exchange barrier (results invalid)   */
 
 /* Finalise + (W>1: exchange through `comm`) + reduce the selected cells, then (reset != 0) reset them; reset == 0 is
  * the per-step "live" exchange: every rank sees the running global value, the epoch keeps accumulating.
+ *   ranges      : the first n_global_ranges select globally-reduced cells (identical layout on every rank, covered by
+ *                 layout_hash, exchanged); the remaining ranges select rank-local cells (never exchanged, may differ
+ *                 between ranks).  The exchange grid is a constant, so ranks with different selections still pair up and
+ *                 a disagreement surfaces as DMLB_METRIC_LAYOUT / SPLIT_VOTE in `status`, not as a stall.
  *   out_val[c]  : 8 bytes — a double (float kinds; already rounded to fp32 when the metric is fp32) or an int64
  *   out_flag[c] : 0 value present, 1 empty (history entry is None)
  *   status      : DMLB_METRIC_STATUS_SLOTS int32 (see above), each DMLB_METRIC_*; out_val / out_flag / status may point
  *                 into device-mapped pinned host memory (results then need no D2H copy)
  * comm may be NULL when world == 1.  layout_hash must be equal on all ranks. */
 int dmlb_metric_reduce(void *comm, uint64_t *acc, int64_t *cnt, const uint32_t *desc, int n_cells,
-                       const dmlb_range *ranges, int n_ranges, uint64_t layout_hash, int reset, uint64_t *out_val,
-                       uint8_t *out_flag, int32_t *status, void *stream);
+                       const dmlb_range *ranges, int n_ranges, int n_global_ranges, uint64_t layout_hash, int reset,
+                       uint64_t *out_val, uint8_t *out_flag, int32_t *status, void *stream);
 /* NCCL/gloo-exchange variant of the cross-rank half: `gathered` = [world][n_sel] records of {val, cnt} produced by
  * dmlb_metric_finalize on each rank and all-gathered by the caller (torch.distributed). */
 int dmlb_metric_finalize(uint64_t *acc, int64_t *cnt, const uint32_t *desc, const dmlb_range *ranges, int n_ranges,

@@ -60,12 +60,14 @@ class OracleAdamLib:
         return np.ctypeslib.as_array((ctype * n).from_address(ptr))
 
     def dmlb_adam_step_f32(self, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled,
-                           maximize, sumsq, max_norm, state, advance, stream):
+                           maximize, sumsq, max_norm, state, advance, lr_dev, stream):
         import ctypes
 
         self.launches += 1
         p, g, m, v = (self._view(x, n, ctypes.c_float) for x in (param, grad, exp_avg, exp_avg_sq))
         st = self._view(state, 2, ctypes.c_int64)
+        if lr_dev:
+            lr = float(self._view(lr_dev, 1, ctypes.c_double)[0])
         coef = 1.0
         if sumsq:
             coef = float(clip_coef(self._view(sumsq, 1, ctypes.c_double)[0], max_norm))
@@ -75,3 +77,18 @@ class OracleAdamLib:
         if advance:
             st[0] += 1
         return 0
+
+
+def sgd_step(p, g, buf, first, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, maximize=False, coef=1.0,
+             dtype=np.float64):
+    """torch/optim/sgd.py _single_tensor_sgd (what the reference's `optimizer.step()`, stage.py:287-288, runs for the
+    ResNet-18 configuration's SGD), with clip_grad_norm_'s coefficient folded in like csrc/optim_kernels.cu K6.
+    `first`: no momentum buffer exists yet (torch clones the gradient into it).  Returns (param, momentum_buffer)."""
+    f = dtype
+    p, g = p.astype(f), g.astype(f) * f(-coef if maximize else coef)
+    if weight_decay != 0:
+        g = g + f(weight_decay) * p
+    if momentum != 0:
+        buf = g.copy() if first else f(momentum) * buf.astype(f) + f(1.0 - dampening) * g
+        g = g + f(momentum) * buf if nesterov else buf
+    return p - f(lr) * g, buf

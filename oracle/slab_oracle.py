@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 MEAN, SUM, MIN, MAX = range(4)
-OK, SPLIT_VOTE, LAYOUT = 0, 1, 2
+OK, SPLIT_VOTE, LAYOUT, TIMEOUT = 0, 1, 2, 3
 
 
 def _world(group=None):
@@ -39,6 +39,9 @@ class _Ready:
 class OracleSlab:
     device = torch.device('cpu')
     comm = None
+    batching = False   # (the device slab queues folds per step; the oracle applies them immediately)
+    feed = None
+    generation = 1
 
     def __init__(self, group=None, capacity=4096):
         self.group = group
@@ -99,6 +102,9 @@ class OracleSlab:
     def flush(self):
         pass
 
+    def flush_all(self):
+        pass
+
     def _fold(self, c, values):
         d = self.desc[c]
         op = self._op(d)
@@ -120,7 +126,7 @@ class OracleSlab:
                 self.acc_f[c] = np.nan if (np.isnan(v).any() or np.isnan(self.acc_f[c])) else max(self.acc_f[c], v.max())
         self.cnt[c] += np.asarray(values).size
 
-    def fold_imm(self, cell, value, is_int):
+    def fold_imm(self, cell, value, is_int, op=SUM):
         self._fold(cell, [value])
 
     def fold_device(self, cell, lanes, k, tensor, steps=1):

@@ -5,9 +5,8 @@
 For every size (the MNIST bucket, the three ResNet-18 DDP buckets, the whole ResNet-18 gradient set) and wire dtype:
   fused   dmlb_comm_allreduce: scale+cast -> peer exchange -> sum -> write-back in ONE kernel.  R launches are captured
           into a CUDA graph and the replay is timed with CUDA events (device time, no host launch latency), max over ranks.
-          Besides the default dispatch (algo 0), messages >= 1 MB are also timed with the two-shot algorithm forced, in
-          its pull (algo 2) and push (algo 4) variants and with the all-push chunk-pipelined kernel (algo 5; its step
-          size comes from DMLB_PUSH_STEP_VECTORS, recorded in the output).
+          Besides the default dispatch (algo 0), messages >= 1 MB are also timed with the one-shot (algo 1), two-shot
+          (algo 2) and — when the arenas are bound to an NVSwitch multicast object — NVLS (algo 3) kernels forced.
   nccl    what the NCCL route costs for the same result: K1 pack (libdmlb) -> ncclAllReduce (torch.distributed) -> K2
           unpack (libdmlb), timed with CUDA events around 20 back-to-back iterations, max over ranks.
 Reported per entry: microseconds, algorithmic bus bandwidth 2(W-1)/W * wire_bytes / time (GB/s) and its fraction of the
@@ -28,8 +27,6 @@ from dmlcloud_b200.gradsync import WIRES, GradBucketSync  # noqa: E402
 from dmlcloud_b200.util import distributed as D  # noqa: E402
 
 NVLINK_GBPS = 770.0
-PIPELINED = os.environ.get('SWEEP_PIPELINED', '0') == '1'  # algo 3: measured slower in round 1, off by default
-PUSH_PIPELINED = os.environ.get('SWEEP_PUSH_PIPELINED', '1') == '1'  # algo 5
 SIZES = [('mnist_cnn', 10_330), ('resnet18_b0', 513_000), ('resnet18_b2', 3_963_456), ('resnet18_b1', 7_213_056),
          ('resnet18_all', 11_689_512)]
 
@@ -53,6 +50,7 @@ def main():
 
     for wire in ('bf16', 'fp32'):
         sync = GradBucketSync(dev, wire=wire, route='peer', max_message_bytes=64 << 20)
+        multicast = sync.comm.multicast
         for name, n in SIZES:
             g = torch.Generator(device='cpu').manual_seed(1000 + rank)
             base = torch.randn(n, generator=g).to(dev)
@@ -64,14 +62,14 @@ def main():
             def time_algo(algo):
                 with torch.cuda.stream(side):
                     st = N.stream_ptr(side)
-                    N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, algo, st))
+                    N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None, algo, None, st))
                     torch.cuda.synchronize()
                     graph = torch.cuda.CUDAGraph()
                     dist.barrier()
                     with torch.cuda.graph(graph, stream=side):
                         for _ in range(R):
                             N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0, None,
-                                                            algo, N.stream_ptr(side)))
+                                                            algo, None, N.stream_ptr(side)))
                     times = []
                     for _ in range(6):
                         dist.barrier()
@@ -85,15 +83,21 @@ def main():
 
             with torch.cuda.stream(side):
                 N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0 / world, None, 0,
-                                                N.stream_ptr(side)))
+                                                None, N.stream_ptr(side)))
                 torch.cuda.synchronize()
                 fused_result = buf.clone()
+                nvls_result = None
+                if sync.comm.multicast:
+                    buf.copy_(base)
+                    N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), n, WIRES[wire], 1.0 / world, None, 3,
+                                                    None, N.stream_ptr(side)))
+                    torch.cuda.synchronize()
+                    nvls_result = buf.clone()
             fused_us = time_algo(0)
             big = wire_bytes >= (1 << 20)
-            pipe_us = time_algo(3) if big and PIPELINED else None  # tile-pipelined one-shot (algo 3)
-            pull_us = time_algo(2) if big else None                # two-shot, reduced slices pulled by the peers
-            push_us = time_algo(4) if big else None                # two-shot, reduced slices pushed by the reducer
-            ppipe_us = time_algo(5) if big and PUSH_PIPELINED else None  # two-shot, all-push, chunk-pipelined (control warps)
+            one_us = time_algo(1) if big else None                          # one-shot forced
+            pull_us = time_algo(2) if big else None                         # two-shot (peer loads) forced
+            nvls_us = time_algo(3) if big and sync.comm.multicast else None  # in-switch reduction forced
             # ---- NCCL route ----
             buf2 = base.clone()
             stage = torch.empty(n, dtype=torch.bfloat16, device=dev) if wire == 'bf16' else None
@@ -123,6 +127,7 @@ def main():
             b.synchronize()
             nccl_us = gather_max(a.elapsed_time(b) * 1e3 / 20)
             diff = float((fused_result - nccl_result).abs().max() / nccl_result.abs().max())
+            nvls_diff = None if nvls_result is None else float((nvls_result - nccl_result).abs().max() / nccl_result.abs().max())
             bus = 2 * (world - 1) / world * wire_bytes
 
             def entry(us):
@@ -131,17 +136,16 @@ def main():
 
             results.append({'bucket': name, 'elements': n, 'wire': wire, 'wire_bytes': wire_bytes,
                             'fused_peer_kernel': entry(fused_us),
-                            'fused_pipelined_oneshot': entry(pipe_us) if pipe_us else None,
-                            'twoshot_pull_forced': entry(pull_us) if pull_us else None,
-                            'twoshot_push_forced': entry(push_us) if push_us else None,
-                            'push_pipelined_forced': entry(ppipe_us) if ppipe_us else None,
+                            'oneshot_forced': entry(one_us) if one_us else None,
+                            'twoshot_forced': entry(pull_us) if pull_us else None,
+                            'nvls_forced': entry(nvls_us) if nvls_us else None,
+                            'rel_diff_nvls_vs_nccl': nvls_diff,
                             'nccl_route_k1_allreduce_k2': entry(nccl_us),
                             'speedup_vs_nccl_route': round(nccl_us / fused_us, 2), 'rel_diff_fused_vs_nccl': diff})
         sync.close()
     if rank == 0:
-        print(json.dumps({'world': world, 'gpu': torch.cuda.get_device_name(dev),
-                          'push_step_vectors': int(os.environ.get('DMLB_PUSH_STEP_VECTORS', '1536')), 'results': results}, indent=1), file=out,
-              flush=True)
+        print(json.dumps({'world': world, 'gpu': torch.cuda.get_device_name(dev), 'multicast': bool(multicast),
+                          'results': results}, indent=1), file=out, flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

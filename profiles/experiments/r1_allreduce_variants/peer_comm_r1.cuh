@@ -1,11 +1,9 @@
-// Peer-memory communicator shared by the fused gradient all-reduce, the fused step exchange and the metric-slab exchange.
+// Peer-memory communicator shared by the fused gradient all-reduce and the metric-slab exchange.
 //
-// Every rank owns one ARENA (cudaMalloc + CUDA IPC, or cuMemCreate + POSIX-fd export when NVSwitch multicast is used),
-// mapped by all peers over NVLink 5 / NVSwitch:
+// Every rank owns one ARENA (cudaMalloc, exported with CUDA IPC, mapped by all peers over NVLink 5 / NVSwitch):
 //
 //   [0      ..  4 KB)   control: seq (u32), done counter (u32), error word (u32)      — touched only by the owner
-//   [4 KB   .. 32 KB)   flags[2 barriers][kMaxCtas][8 ranks] u32                      — written by peers, read by owner
-//   [32 KB  .. 64 KB)   mstage[2 halves][16 KB]     metric records of the fused step exchange — read by peers
+//   [4 KB   .. 64 KB)   flags[4 regions][kMaxCtas][8 ranks] u32                       — written by peers, read by owner
 //   [64 KB  .. +2*M )   stage[2 halves][M bytes]    this rank's scaled/cast message   — read by peers
 //   [ ...   .. +2*M )   result[2 halves][M bytes]   two-shot: this rank's reduced slice — read by peers
 //
@@ -18,11 +16,6 @@
 // CTA b on rank A pairs only with CTA b on the peers (it reads exactly the index range their CTA b wrote), so no
 // grid-wide barrier is needed; all ranks must launch the same grid for the same collective (deterministic in n, W).
 // A communicator must be driven from ONE stream at a time; the gradient path and the metric path own separate ones.
-//
-// Dead peers: a barrier gives up after `timeout_ns` (default 10 minutes, like NCCL's watchdog; dmlb_comm_configure), sets
-// the sticky error word in the arena AND — when configured — a word in device-mapped pinned host memory that the host
-// polls every step without any synchronisation, and the kernel POISONS its outputs (NaN gradients, TIMEOUT metric status)
-// instead of writing a plausible partial sum.
 #pragma once
 #include "dmlb_common.cuh"
 
@@ -30,23 +23,17 @@ namespace dmlb {
 
 constexpr int kMaxCtas = 296;  // 2 per SM on 148 SMs
 constexpr size_t kCtrlBytes = 4096;
-constexpr int kFlagRegions = 2;  // the two per-collective barriers
+constexpr int kFlagRegions = 4;  // 0, 1: the per-collective barriers; 2, 3: per-chunk flags of the pipelined all-reduces
 constexpr size_t kFlagBytes = (size_t)kFlagRegions * kMaxCtas * DMLB_MAX_WORLD * sizeof(uint32_t);
-constexpr size_t kMetricStageOff = 32768;
-constexpr size_t kMetricStageBytes = 16384;  // per half: 16-byte header + 16 B per exchanged cell
 constexpr size_t kHeaderBytes = 65536;
-static_assert(kCtrlBytes + kFlagBytes <= kMetricStageOff, "arena header: flags");
-static_assert(kMetricStageOff + 2 * kMetricStageBytes <= kHeaderBytes, "arena header: metric staging");
+static_assert(kCtrlBytes + kFlagBytes <= kHeaderBytes, "arena header");
 constexpr int kCommThreads = 256;
-constexpr int kStepMetricMaxCells = (int)(kMetricStageBytes / 16) - 1;
 
 struct CommDev {
     int world, rank;
     size_t msg_cap;  // M: bytes per stage half
     unsigned char *arena[DMLB_MAX_WORLD];
-    unsigned char *mc;  // multicast mapping of the arenas (NVSwitch in-switch reduction), or nullptr
     unsigned long long timeout_ns;
-    uint32_t *host_err;  // device address of a mapped pinned host word (or nullptr)
 
     __device__ __forceinline__ uint32_t *seq() const { return reinterpret_cast<uint32_t *>(arena[rank]); }
     __device__ __forceinline__ uint32_t *done() const { return reinterpret_cast<uint32_t *>(arena[rank]) + 1; }
@@ -55,17 +42,11 @@ struct CommDev {
         return reinterpret_cast<uint32_t *>(arena[r] + kCtrlBytes) +
                ((size_t)barrier * kMaxCtas + cta) * DMLB_MAX_WORLD;
     }
-    __device__ __forceinline__ unsigned char *mstage(int r, int half) const {
-        return arena[r] + kMetricStageOff + (size_t)half * kMetricStageBytes;
-    }
     __device__ __forceinline__ unsigned char *stage(int r, int half) const {
         return arena[r] + kHeaderBytes + (size_t)half * msg_cap;
     }
     __device__ __forceinline__ unsigned char *result(int r, int half) const {
         return arena[r] + kHeaderBytes + 2 * msg_cap + (size_t)half * msg_cap;
-    }
-    __device__ __forceinline__ unsigned char *mc_stage(int half) const {
-        return mc + kHeaderBytes + (size_t)half * msg_cap;
     }
 };
 
@@ -97,34 +78,22 @@ __device__ __forceinline__ uint32_t comm_begin(const CommDev &c) {
 
 // Per-CTA barrier `which` (0 or 1) of collective s.  All threads of the CTA must call.  On entry every thread's prior
 // global writes are published to the peers; on exit the peers' writes (made before their arrival) are visible.
-// Returns false (to every thread of the CTA) when a peer did not arrive in time: the caller must poison its outputs.
-__device__ __forceinline__ bool comm_barrier(const CommDev &c, int which, uint32_t s) {
+__device__ __forceinline__ void comm_barrier(const CommDev &c, int which, uint32_t s) {
     __syncthreads();
-    int failed = 0;
     if (threadIdx.x < c.world) {
         const int peer = threadIdx.x;
         __threadfence_system();
         st_release_sys(c.flags(peer, which, blockIdx.x) + c.rank, s);
         const uint32_t *mine = c.flags(c.rank, which, blockIdx.x) + peer;
         const unsigned long long t0 = globaltimer_ns();
-        unsigned int spins = 0;
         while ((int32_t)(ld_acquire_sys(mine) - s) < 0) {
-            if ((++spins & 1023u) == 0u) {
-                // a peer that already failed never arrives: give up as soon as the sticky error word is set
-                const bool dead = *reinterpret_cast<volatile uint32_t *>(c.err()) != 0u;
-                if (dead || globaltimer_ns() - t0 > c.timeout_ns) {
-                    atomicExch(c.err(), 1u);
-                    if (c.host_err) {
-                        *reinterpret_cast<volatile uint32_t *>(c.host_err) = 1u;
-                        __threadfence_system();
-                    }
-                    failed = 1;
-                    break;
-                }
+            if (globaltimer_ns() - t0 > c.timeout_ns) {  // a peer died: record it and fall through instead of hanging
+                atomicExch(c.err(), 1u);
+                break;
             }
         }
     }
-    return __syncthreads_or(failed) == 0;
+    __syncthreads();
 }
 
 // Last CTA out publishes seq = s for the next collective on this stream.

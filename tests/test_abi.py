@@ -24,7 +24,7 @@ def test_library_builds_and_loads_without_gpu():
     so = build.build()
     assert so.exists()
     lib = N.load()
-    assert lib.dmlb_abi_version() == 1
+    assert lib.dmlb_abi_version() == N.ABI_VERSION == 2
 
 
 def test_header_symbols_are_exported_and_bound():
@@ -42,7 +42,13 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(N.FoldEntry) == 40
     assert ctypes.sizeof(N.Seg) == 24
     assert ctypes.sizeof(N.Range) == 8
+    # dmlb_step_metrics: 6 pointers + u64 + 8 x i32 + 32 fold entries + 64 ranges (static_assert'ed in csrc/peer_comm.cu)
+    assert ctypes.sizeof(N.StepMetrics) == 1880
     text = HEADER.read_text()
+    assert f'#define DMLB_FEED_WIDTH {N.FEED_WIDTH}' in text
+    assert f'#define DMLB_SRC_FEED {N.SRC_FEED}' in text
+    assert f'#define DMLB_STEP_METRIC_MAX_CELLS {N.STEP_METRIC_MAX_CELLS}' in text
+    assert f'#define DMLB_ABI_VERSION {N.ABI_VERSION}' in text
     assert f'#define DMLB_MAX_RANGES {N.MAX_RANGES}' in text
     assert f'#define DMLB_MAX_FOLD_ENTRIES {N.MAX_FOLD_ENTRIES}' in text
     assert f'#define DMLB_MAX_WORLD {N.MAX_WORLD}' in text
@@ -68,15 +74,25 @@ def test_argument_validation_needs_no_gpu():
     arenas = (ctypes.c_void_p * 1)(None)
     assert lib.dmlb_comm_create(ctypes.byref(comm), 9, 0, arenas, 1024) == N.EINVAL
     assert lib.dmlb_comm_create(ctypes.byref(comm), 1, 0, arenas, 1024) == N.EALIGN
-    # K5: 17 arguments (doubles for the hyper-parameters) marshalled through ctypes; rejected before any CUDA call
+    # K5: 18 arguments (doubles for the hyper-parameters) marshalled through ctypes; rejected before any CUDA call
     a = ctypes.c_void_p(256)
     adam = lambda p, state, beta1, n=16: lib.dmlb_adam_step_f32(p, a, a, a, n, 1e-3, beta1, 0.999, 1e-8, 0.0, 0, 0, None,  # noqa: E731
-                                                                0.0, state, 1, None)
+                                                                0.0, state, 1, None, None)
     assert adam(a, None, 0.9) == N.EINVAL          # no state block
     assert adam(None, a, 0.9) == N.EINVAL          # no parameters
     assert adam(a, a, 1.0) == N.EINVAL             # beta1 outside [0, 1)
     assert adam(ctypes.c_void_p(258), a, 0.9) == N.EALIGN
     assert adam(a, ctypes.c_void_p(260), 0.9) == N.EALIGN  # the state block holds an int64
+    # K6 and the communicator knobs: rejected before any CUDA call as well
+    sgd = lambda p, buf, mom, nest=0: lib.dmlb_sgd_step_f32(p, a, buf, 16, 0.1, mom, 0.0, 0.0, nest, 0, None, 0.0, a, 1,  # noqa: E731
+                                                          None, None)
+    assert sgd(None, a, 0.9) == N.EINVAL
+    assert sgd(a, None, 0.9) == N.EINVAL           # momentum without a momentum buffer
+    assert sgd(a, a, 0.0, 1) == N.EINVAL           # nesterov needs momentum
+    assert lib.dmlb_comm_configure(None, 1.0, None) == N.EINVAL
+    assert lib.dmlb_comm_allreduce(None, a, 16, N.WIRE_BF16, 1.0, None, 0, None, None) == N.EINVAL
+    # the driver VMM entry points resolve lazily: without a driver they report "not connected" instead of crashing
+    assert lib.dmlb_vmm_granularity(0, 2) == 0 or lib.dmlb_vmm_granularity(0, 2) >= (1 << 16)
 
 
 def test_product_refuses_to_compute_without_cuda():

@@ -122,7 +122,7 @@ def _allreduce_worker(rank, world, initfile, outdir, cases):
                 fut.wait()
             else:  # force one-shot (1) / two-shot (2) regardless of size
                 N.check(lib.dmlb_comm_allreduce(sync.comm.handle, buf.data_ptr(), buf.numel(), WIRES[wire], 1.0 / world,
-                                                sync.sumsq.data_ptr(), algo, N.stream_ptr()), 'allreduce')
+                                                sync.sumsq.data_ptr(), algo, None, N.stream_ptr()), 'allreduce')
             torch.cuda.synchronize()
             got = buf.cpu().numpy()
             twoshot = algo in (2, 4, 5) or (algo == 0 and world > 2 and buf.numel() * (2 if wire == 'bf16' else 4) > 512 * 1024)

@@ -62,12 +62,12 @@ def test_adam_kernel_vs_oracle(n, cfg):
                 N.check(lib.dmlb_adam_step_f32(scratch[0].data_ptr(), g.data_ptr(), scratch[1].data_ptr(),
                                                scratch[2].data_ptr(), n, c['lr'], c['betas'][0], c['betas'][1], c['eps'],
                                                c['weight_decay'], int(c['decoupled']), int(c['maximize']), None, 0.0,
-                                               state.data_ptr(), 0, st), 'adam(no advance)')
+                                               state.data_ptr(), 0, None, st), 'adam(no advance)')
                 assert int(state[0].item()) == t - 1
             N.check(lib.dmlb_adam_step_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, c['lr'],
                                            c['betas'][0], c['betas'][1], c['eps'], c['weight_decay'], int(c['decoupled']),
                                            int(c['maximize']), sumsq.data_ptr() if clip is not None else None,
-                                           clip or 0.0, state.data_ptr(), 1, st), 'adam')
+                                           clip or 0.0, state.data_ptr(), 1, None, st), 'adam')
             Pd, M, V = adam_oracle.adam_step(Pd, G, M, V, t, lr=c['lr'], betas=c['betas'], eps=c['eps'],
                                              weight_decay=c['weight_decay'], decoupled=c['decoupled'],
                                              maximize=c['maximize'], coef=coef)
