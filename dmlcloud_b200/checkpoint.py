@@ -126,3 +126,82 @@ class CheckpointDir:
         import torch
 
         return torch.load(self._state_path(tag), map_location=map_location, weights_only=False)
+
+
+class AsyncSnapshot:
+    """Asynchronous state snapshots: device -> staging arena (same stream as the training step) -> pinned
+    host memory (side stream) -> file (writer thread).  One snapshot is in flight at a time; the staging buffers are
+    reused, so a new `save` first waits for the previous write (normally long finished)."""
+
+    def __init__(self, checkpoint_dir, device):
+        import threading
+
+        import torch
+
+        self.dir = checkpoint_dir
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == 'cuda' else None
+        self._staging = {}  # path in the state tree -> (device copy, pinned host copy)
+        self._thread = None
+        self._error = None
+        self._lock = threading.Lock()
+        self.written = 0
+
+    def _stage(self, obj, path, copies):
+        import torch
+
+        if isinstance(obj, torch.Tensor):
+            if not obj.is_cuda:
+                return obj
+            slot = self._staging.get(path)
+            if slot is None or slot[0].shape != obj.shape or slot[0].dtype != obj.dtype:
+                slot = (torch.empty_like(obj, memory_format=torch.contiguous_format),
+                        torch.empty(obj.shape, dtype=obj.dtype, pin_memory=True))
+                self._staging[path] = slot
+            slot[0].copy_(obj, non_blocking=True)  # D2D on the caller's stream: the original may change right after
+            copies.append(slot)
+            return slot[1]
+        if isinstance(obj, dict):
+            return {k: self._stage(v, f'{path}/{k}', copies) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            out = [self._stage(v, f'{path}/{i}', copies) for i, v in enumerate(obj)]
+            return out if isinstance(obj, list) else tuple(out)
+        return obj
+
+    def save(self, state, tags):
+        import threading
+
+        import torch
+
+        self.wait()
+        copies = []
+        host_state = self._stage(state, '', copies)
+        event = None
+        if self.stream is not None and copies:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                for dev_copy, host_copy in copies:
+                    host_copy.copy_(dev_copy, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record()
+
+        def write():
+            try:
+                if event is not None:
+                    event.synchronize()
+                for tag in tags:
+                    self.dir.save_state(host_state, tag)
+                self.written += 1
+            except Exception as exc:  # noqa: BLE001 - surfaced by the next wait()
+                self._error = exc
+
+        self._thread = threading.Thread(target=write, name='dmlcloud-snapshot', daemon=True)
+        self._thread.start()
+
+    def wait(self):
+        t, self._thread = self._thread, None
+        if t is not None:
+            t.join()
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err

@@ -119,7 +119,8 @@ STATUS_BYTES = 4 * N.METRIC_STATUS_SLOTS  # one int32 status slot per CTA of a r
 
 class _PendingResult:
     """Results of one reduce launch on their way to the host: the kernel writes them straight into mapped pinned host
-    memory (or they are copied there), and an event marks completion."""
+    memory (or they are copied there), and an event marks completion.  The block belongs to a small ring owned by the
+    slab; whoever needs the block next parses this result out of it first (`get()`), so nothing is ever lost."""
 
     def __init__(self, slab, host, event, capacity):
         self.slab, self.host, self.event, self.capacity = slab, host, event, capacity
@@ -135,8 +136,7 @@ class _PendingResult:
             status = int(self.host[:STATUS_BYTES].view(torch.int32).max())
             vals = self.host[STATUS_BYTES:STATUS_BYTES + 8 * cap].view(torch.int64).clone()
             flags = self.host[STATUS_BYTES + 8 * cap:STATUS_BYTES + 9 * cap].clone()
-            self.slab._release_host(self.host, self.event)
-            self.host = self.event = None
+            self.host = None  # the ring slot may be reused from here on
             self._parsed = (status, vals, flags)
         return self._parsed
 
@@ -297,10 +297,9 @@ class DeviceSlab:
         self.capacity = 0
         self.n_cells = 0
         self.acc = self.cnt = self.desc = self.out = None
-        self._host_pool = []
-        self._event_pool = []
+        self._host_pool = []  # ring of pinned result blocks (see _acquire_host)
+        self._host_next = 0
         self._wr = None
-        self._host_dptr = {}
         self._range_cache = {}
         self._host_mapped = None  # None = not probed yet; False = pinned memory is not device-mapped here (copy path)
         self._imm = []           # queued fold entries (immediates, and device values while batching)
@@ -327,7 +326,11 @@ class DeviceSlab:
         self.out = torch.zeros(STATUS_BYTES + 9 * capacity, dtype=torch.uint8, device=self.device)
         self.capacity = capacity
         self._ptrs = (self.acc.data_ptr(), self.cnt.data_ptr(), self.desc.data_ptr(), self.out.data_ptr())
+        for slot in getattr(self, '_host_pool', []):  # results still sitting in blocks of the old size: read them out
+            if slot['pending'] is not None:
+                slot['pending'].get()
         self._host_pool = []
+        self._host_next = 0
         self.generation += 1
 
     def _lib(self):
@@ -354,34 +357,38 @@ class DeviceSlab:
         self.flush()
         self.n_cells = n_cells
 
+    HOST_RING = 8
+
     def _acquire_host(self):
-        """(pinned host block, device address of it or None).  Blocks are pooled; status slots are zero on hand-out."""
+        """(pinned host block, device address of it or None, its event).  The blocks form a fixed ring (no allocation and
+        no cudaHostAlloc stall in steady state: the p99 of r1's per-step exchange was exactly that); a block whose previous
+        result has not been read yet is parsed out first.  Status slots are zero on hand-out."""
         size = STATUS_BYTES + 9 * self.capacity
-        while self._host_pool:
-            host, dptr = self._host_pool.pop()
-            if host.numel() == size:
-                return host, dptr
-        host = torch.zeros(size, dtype=torch.uint8, pin_memory=True)
-        dptr = None
-        if self._host_mapped is not False:
-            out = ctypes.c_void_p()
-            rc = self._lib().dmlb_host_device_pointer(host.data_ptr(), ctypes.byref(out))
-            self._host_mapped = rc == N.OK and bool(out.value)
-            dptr = out.value if self._host_mapped else None
-        self._host_dptr[host.data_ptr()] = dptr
-        return host, dptr
-
-    def _release_host(self, host, event=None):
-        if event is not None and len(self._event_pool) < 64:
-            self._event_pool.append(event)
-        if host.numel() == STATUS_BYTES + 9 * self.capacity and len(self._host_pool) < 16:
-            host[:STATUS_BYTES].zero_()
-            self._host_pool.append((host, self._host_dptr.get(host.data_ptr())))
-        else:
-            self._host_dptr.pop(host.data_ptr(), None)
-
-    def _event(self):
-        return self._event_pool.pop() if self._event_pool else torch.cuda.Event()
+        ring = self._host_pool
+        if not ring or ring[0]['host'].numel() != size:
+            for slot in ring:
+                if slot['pending'] is not None:
+                    slot['pending'].get()
+            ring = self._host_pool = []
+            self._host_next = 0
+        if len(ring) < self.HOST_RING:
+            host = torch.zeros(size, dtype=torch.uint8, pin_memory=True)
+            dptr = None
+            if self._host_mapped is not False:
+                out = ctypes.c_void_p()
+                rc = self._lib().dmlb_host_device_pointer(host.data_ptr(), ctypes.byref(out))
+                self._host_mapped = rc == N.OK and bool(out.value)
+                dptr = out.value if self._host_mapped else None
+            slot = {'host': host, 'dptr': dptr, 'event': torch.cuda.Event(), 'pending': None}
+            ring.append(slot)
+            return slot
+        slot = ring[self._host_next % self.HOST_RING]
+        self._host_next += 1
+        old = slot['pending']
+        if old is not None and old.host is not None:
+            old.get()  # copy the unread result out of the block before it is overwritten (its event is long complete)
+        slot['host'][:STATUS_BYTES].zero_()
+        return slot
 
     # -- fold --------------------------------------------------------------------------------------------------------
     def fold_imm(self, cell, value, is_int, op=N.SUM):
@@ -485,15 +492,15 @@ class DeviceSlab:
         if not exchange:
             world = 1
         st = N.stream_ptr()
-        host = None
+        slot = None
         acc_p, cnt_p, desc_p, out_p = self._ptrs
         base = out_p
         if to_host:
-            host, dptr = self._acquire_host()
-            if dptr is not None:
-                base = dptr  # the kernel writes its results straight into mapped pinned host memory
+            slot = self._acquire_host()
+            if slot['dptr'] is not None:
+                base = slot['dptr']  # the kernel writes its results straight into mapped pinned host memory
         status_ptr, val_ptr, flag_ptr = base, base + STATUS_BYTES, base + STATUS_BYTES + 8 * self.capacity
-        if base == out_p:  # device-resident block: clear the sticky status slots (pooled host blocks are handed out zeroed)
+        if base == out_p:  # device-resident block: clear the sticky status slots (ring blocks are handed out zeroed)
             N.check(lib.dmlb_memset_async(status_ptr, 0, STATUS_BYTES, st), 'memset(status)')
 
         def launch(comm_handle, glob, loc):
@@ -530,10 +537,11 @@ class DeviceSlab:
         if not to_host:
             return None
         if base == out_p:  # pinned memory not device-mapped on this platform: one D2H copy instead
-            host.copy_(self.out, non_blocking=True)
-        event = self._event()
-        event.record()
-        return _PendingResult(self, host, event, self.capacity)
+            slot['host'].copy_(self.out, non_blocking=True)
+        slot['event'].record()
+        pending = _PendingResult(self, slot['host'], slot['event'], self.capacity)
+        slot['pending'] = pending
+        return pending
 
     def _reduce_via_collective(self, lib, ranges, layout_hash, reset, world, rank, val_ptr, flag_ptr, status_ptr, st):
         """Exchange through torch.distributed (NCCL all_gather of the packed record) when no peer arena is attached.
@@ -563,7 +571,7 @@ class DeviceSlab:
             gathered.copy_(torch.cat(cpu))
         N.check(lib.dmlb_metric_combine(gathered.data_ptr(), world, rank, self.desc.data_ptr(), arr, len(ranges),
                                         val_ptr, flag_ptr, status_ptr, N.stream_ptr()), 'metric_combine')
-        self._keep = (record, gathered)
+        self._collective_keep = (record, gathered)
 
     def result_view(self, cell, lanes, is_int):
         """Device view of the last reduce's values for cells [cell, cell+lanes) (no host sync)."""
@@ -571,9 +579,12 @@ class DeviceSlab:
         return vals[cell:cell + lanes]
 
     # -- checkpoint --------------------------------------------------------------------------------------------------
-    def export_cells(self, cell, lanes):
+    def export_cells(self, cell, lanes, device_tensors=False):
         self.flush_all()
-        return self.acc[cell:cell + lanes].cpu(), self.cnt[cell:cell + lanes].cpu()
+        acc, cnt = self.acc[cell:cell + lanes], self.cnt[cell:cell + lanes]
+        if device_tensors:  # (an asynchronous snapshot stages them to the host itself: no sync here)
+            return acc.clone(), cnt.clone()
+        return acc.cpu(), cnt.cpu()
 
     def import_cells(self, cell, acc, cnt):
         self.acc[cell:cell + acc.numel()].copy_(acc)
@@ -861,11 +872,11 @@ class SlabMetric:
     def layout_item(self):
         return (self.name, self.lanes, self.reduction.value, str(self.dtype), bool(self.globally))
 
-    def state_dict(self):
+    def state_dict(self, device_tensors=False):
         state = {'reduction': self.reduction, 'dim': self.dim, 'globally': self.globally, 'values': [],
                  'count': self.count, 'partial': None}
         if self.cell is not None:
-            acc, cnt = self._tracker._slab_or_create().export_cells(self.cell, self.lanes)
+            acc, cnt = self._tracker._slab_or_create().export_cells(self.cell, self.lanes, device_tensors)
             state['partial'] = {'acc': acc, 'cnt': cnt, 'shape': self.value_shape, 'dtype': self.dtype}
         return state
 
@@ -1146,13 +1157,13 @@ class MetricTracker:
         self.epoch += 1
 
     # -- checkpoint (reference 282-296) ------------------------------------------------------------------------------
-    def state_dict(self):
+    def state_dict(self, device_tensors=False):
         return {
             'epoch': self.epoch,
             # per-metric lists are copied: the reference hands out its live lists (metrics.py:285), which lets a
             # restored tracker and its source grow each other's histories
             'histories': {name: list(history) for name, history in self.histories.items()},
-            'reducers': {name: reducer.state_dict() for name, reducer in self.reducers.items()},
+            'reducers': {name: reducer.state_dict(device_tensors) for name, reducer in self.reducers.items()},
         }
 
     def load_state_dict(self, state):

@@ -114,6 +114,7 @@ class _FlatBase(torch.optim.Optimizer):
                 raise RuntimeError(f'{type(self).__name__}: a parameter no longer aliases the flat buffer (its .data was '
                                    'replaced)')
             lib = self._lib(flat['device'])
+            flat['stepped'] = True  # host-side "a step has been issued": state_dict() then has state without a device read
             clip_args = (clip[0].data_ptr(), float(clip[1])) if clip is not None else (None, 0.0)
             st = N.stream_ptr() if self._lib_override is None else None
             base = self._flat_grad_base(group, flat)
@@ -168,13 +169,15 @@ class FlatAdam(_FlatBase):
 
     # -- checkpoint: torch.optim.Adam's format -----------------------------------------------------------------------
     def state_dict(self):
+        """torch.optim.Adam's format.  No host synchronisation: `step` stays a device tensor (torch's capturable Adam keeps
+        it on the device too), so an asynchronous snapshot can stage everything in one go."""
         state, groups, index = {}, [], 0
         for group, flat in zip(self.param_groups, self._flat):
-            step = flat['state'][0].to(torch.float32).cpu()
+            step = flat['state'][0].to(torch.float32)
             ids = []
             for p, off in zip(group['params'], flat['offsets']):
                 n = p.numel()
-                if int(step) > 0:
+                if flat.get('stepped'):  # (torch's Adam has no state before its first step either)
                     state[index] = {'step': step.clone(),
                                     'exp_avg': flat['exp_avg'][off:off + n].view(p.shape).clone(),
                                     'exp_avg_sq': flat['exp_avg_sq'][off:off + n].view(p.shape).clone()}
@@ -209,6 +212,7 @@ class FlatAdam(_FlatBase):
                 raise ValueError(f'FlatAdam keeps one step count per group; the loaded state has {sorted(steps)}')
             flat['state'].zero_()
             flat['state'][0] = steps.pop() if steps else 0
+            flat['stepped'] = bool(state_dict['state'])
 
 
 class FlatSGD(_FlatBase):
@@ -244,7 +248,7 @@ class FlatSGD(_FlatBase):
     def state_dict(self):
         state, groups, index = {}, [], 0
         for group, flat in zip(self.param_groups, self._flat):
-            stepped = int(flat['state'][0].item()) > 0
+            stepped = bool(flat.get('stepped'))
             ids = []
             for p, off in zip(group['params'], flat['offsets']):
                 if stepped and group['momentum'] != 0:
@@ -253,7 +257,7 @@ class FlatSGD(_FlatBase):
                 index += 1
             packed = {k: v for k, v in group.items() if k != 'params'}
             packed['params'] = ids
-            packed['_flat_steps'] = int(flat['state'][0].item())  # (torch's SGD keeps no step count; K6 needs "first step?")
+            packed['_flat_steps'] = flat['state'][0].clone()  # (torch's SGD keeps no step count; K6 needs "first step?")
             groups.append(packed)
         return {'state': state, 'param_groups': groups}
 
@@ -276,3 +280,4 @@ class FlatSGD(_FlatBase):
                 seen = True
             flat['state'].zero_()
             flat['state'][0] = int(saved.get('_flat_steps', 1 if seen else 0))
+            flat['stepped'] = seen or int(flat['state'][0]) > 0

@@ -74,6 +74,9 @@ class TrainingPipeline:
         self.compute_stream = None         # dedicated stream all stage work runs on (created in run())
         self._pending_state = {'models': {}, 'optimizers': {}, 'schedulers': {}}  # resumed state awaiting registration
         self._save_policy = {}
+        self._resume_stage_index = 0       # stages before this one were finished by the run a snapshot came from
+        self._snapshot = None              # checkpoint.AsyncSnapshot (pinned staging + writer thread), made on first use
+        self.last_checkpoint_ms = None     # host time the epoch loop spent on the latest snapshot
 
     @property
     def checkpointing_enabled(self):
@@ -201,9 +204,12 @@ class TrainingPipeline:
         with _RunGuard(self):
             self._pre_run()
             with self._on_compute_stream():
-                for stage in self.stages:
+                for index, stage in enumerate(self.stages):
+                    if index < self._resume_stage_index:
+                        continue  # finished before the snapshot this run resumed from was taken
                     self.current_stage = stage
                     stage.run()
+            self.wait_for_checkpoints()
             self._post_run()
 
     def _on_compute_stream(self):
@@ -325,13 +331,15 @@ class TrainingPipeline:
             self._save_epoch_state()
 
     # ---- state snapshots ------------------------------------------------------------------------------
-    def state_dict(self):
+    def state_dict(self, device_tensors=False):
+        """Everything a resumed run needs.  device_tensors=True keeps the metric slab's partial sums on the device (the
+        asynchronous snapshot stages them to pinned memory itself, without a host sync)."""
         stage = self.current_stage
         return {
             'models': {k: _bare(m).state_dict() for k, m in self.models.items()},
             'optimizers': {k: o.state_dict() for k, o in self.optimizers.items()},
             'schedulers': {k: s.state_dict() for k, s in self.schedulers.items()},
-            'tracker': self.tracker.state_dict(),
+            'tracker': self.tracker.state_dict(device_tensors=device_tensors),
             'stage_index': self.stages.index(stage) if stage in self.stages else None,
             'stage_epoch': None if stage is None else stage.current_epoch,
         }
@@ -356,21 +364,33 @@ class TrainingPipeline:
         idx, epoch = state.get('stage_index'), state.get('stage_epoch')
         if idx is not None and epoch is not None and idx < len(self.stages):
             self.stages[idx].current_epoch = epoch
+            self._resume_stage_index = idx  # run() skips the stages the interrupted run had already finished
 
     def load_checkpoint(self, tag: str = 'latest', strict=True):
         """resume_run() helper: load `state/<tag>.pt` from the checkpoint directory (every rank reads the same file).
         Returns False when the directory holds no such snapshot."""
+        self.wait_for_checkpoints()
         if not self.checkpointing_enabled or not self.checkpoint_dir.has_state(tag):
             return False
         self.load_state_dict(self.checkpoint_dir.load_state(tag), strict=strict)
         return True
 
     def _save_epoch_state(self):
-        """End of epoch, metrics already reduced.  All ranks assemble the state (the tracker export is a plain D2H
-        copy, no collective); rank 0 writes the files the register_model save_* arguments ask for."""
+        """End of epoch, metrics already reduced: write the snapshots the register_model save_* arguments ask for
+        (accepted and ignored by the reference, pipeline.py:61-64) — OFF the critical path:
+
+          compute stream   device-to-device copy of every state tensor into a staging arena (microseconds; the next
+                           step may then overwrite parameters and moments at once)
+          side stream      staging arena -> pinned host memory, overlapping the following training steps
+          writer thread    (rank 0) waits for the copy's event, torch.save + atomic rename
+
+        Every rank decides the tags (same tracker values everywhere); only rank 0 copies and writes."""
+        import time
+
         stage = self.current_stage
         if stage is None or not self._save_policy:
             return
+        began = time.perf_counter()
         done = stage.current_epoch
         tags = set()
         for name, pol in self._save_policy.items():
@@ -384,13 +404,20 @@ class TrainingPipeline:
                 if score is not None and (pol['best_value'] is None or score < pol['best_value']):
                     pol['best_value'] = score
                     tags.add(f'best_{name}')
-        if not tags:
-            return
-        state = self.state_dict()
-        state['stage_epoch'] = done + 1  # the epoch a resumed run starts with
-        if is_root():
-            for tag in sorted(tags):
-                self.checkpoint_dir.save_state(state, tag)
+        if tags and is_root():
+            from .checkpoint import AsyncSnapshot
+
+            if self._snapshot is None:
+                self._snapshot = AsyncSnapshot(self.checkpoint_dir, self.device)
+            state = self.state_dict(device_tensors=True)
+            state['stage_epoch'] = done + 1  # the epoch a resumed run starts with
+            self._snapshot.save(state, sorted(tags))
+        self.last_checkpoint_ms = (time.perf_counter() - began) * 1e3
+
+    def wait_for_checkpoints(self):
+        """Block until every snapshot handed to the writer thread is on disk (end of run, before a load)."""
+        if self._snapshot is not None:
+            self._snapshot.wait()
 
     def _cleanup(self, exc_type, exc_value, traceback):
         """End of run(), normal or not (called by _RunGuard)."""
@@ -404,6 +431,10 @@ class TrainingPipeline:
 
             if wandb.run is not None:
                 wandb.finish(exit_code=0 if exc_type is None else 1)
+        try:
+            self.wait_for_checkpoints()
+        except Exception:  # noqa: BLE001 - a failed background write must not mask the run's own exception
+            self.logger.exception('a state snapshot could not be written')
         if self.io_redirector is not None:
             self.io_redirector.uninstall()
         return False  # never swallow the exception

@@ -92,6 +92,21 @@ class EpochTable:
     def __setitem__(self, display_name, value):
         self.backend[display_name] = value
 
+    # the reference hands stages the ProgressTable itself (stage.py:147): user code written against it keeps working
+    def __getitem__(self, display_name):
+        return self.backend[display_name]
+
+    def update(self, display_name, value, **kwargs):
+        self.backend.update(display_name, value, **kwargs)
+
+    def add_column(self, display_name, **kwargs):
+        if not self.has(display_name):
+            self.columns.append({'name': display_name, 'metric': None})
+        self.backend.add_column(display_name, **kwargs)
+
+    def next_row(self, **kwargs):
+        self.backend.next_row(**kwargs)
+
     def emit_row(self, tracker):
         for col in self.columns:
             if col['metric'] is not None:

@@ -6,7 +6,8 @@ under oracle/shims/) on torch.distributed/gloo CPU and writes small fixtures to 
   shard_indices.json     reference util/data.py:11-30 known answers (incl. shuffled, seeds, ShardedSequenceDataset epochs)
   metrics_w{1,2,4}.json  a scripted MetricTracker session (script + every rank's resulting histories), metrics.py
   grads_*.npz            per-rank local gradients (inputs) and the DDP(gloo)-reduced gradients (reference output)
-  train_w{1,2}.json      a short TrainValStage + DDP(gloo) MNIST-CNN run on synthetic data: full tracker.histories
+  train_w{1,2,4,8}.json  a short TrainValStage + DDP(gloo) MNIST-CNN run on synthetic data: full tracker.histories
+  train_clip_w{1,2}.json the same run with gradient_clip() != 0;  train_sched_w1.json with a StepLR scheduler
 
 Usage (build container only):  python oracle/gen_golden.py
 Nothing on the GPU box may call this: /root/reference does not exist there; tests read the committed fixtures.
@@ -240,7 +241,12 @@ def synthetic_batches(seed, steps, batch=BATCH):
             for _ in range(steps)]
 
 
-def _train_worker(rank, world, initfile, outdir):
+CLIP_NORM = 0.05  # small enough that the coefficient is < 1 on most steps of the synthetic run
+
+
+def _train_worker(rank, world, initfile, outdir, variant='plain'):
+    """variant: 'plain' | 'clip' (gradient_clip() = CLIP_NORM, stage.py:256-285) | 'sched' (StepLR stepped per epoch,
+    stage.py:316-318, three epochs so that two different learning rates are applied)."""
     _init(rank, world, initfile)
     from dmlcloud.pipeline import TrainingPipeline
     from dmlcloud.stage import TrainValStage
@@ -251,8 +257,13 @@ def _train_worker(rank, world, initfile, outdir):
             self.pipeline.register_dataset('val', synthetic_batches(200 + rank, VAL_STEPS), verbose=False)
             model, _, _ = make_model('mnist_cnn')
             self.pipeline.register_model('cnn', model, verbose=False)
-            self.pipeline.register_optimizer('adam', torch.optim.Adam(model.parameters(), lr=1e-3))
+            optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)
+            scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=1, gamma=0.5) if variant == 'sched' else None
+            self.pipeline.register_optimizer('adam', optimizer, scheduler)
             self.loss = torch.nn.CrossEntropyLoss()
+
+        def gradient_clip(self):
+            return CLIP_NORM if variant == 'clip' else 0.0
 
         def step(self, batch):
             img, target = batch
@@ -266,7 +277,7 @@ def _train_worker(rank, world, initfile, outdir):
 
     pipeline = TrainingPipeline(name='golden')
     stage = MNISTStage()
-    pipeline.append_stage(stage, max_epochs=EPOCHS)
+    pipeline.append_stage(stage, max_epochs=EPOCHS + (1 if variant == 'sched' else 0))
     with contextlib.redirect_stdout(io.StringIO()):
         pipeline.run()
     hist = {k: [enc(v) for v in h] for k, h in pipeline.tracker.histories.items()}
@@ -278,13 +289,20 @@ def _train_worker(rank, world, initfile, outdir):
 
 
 def gen_train():
-    for world in (1, 2):
-        out = _spawn(_train_worker, world)
+    runs = [('plain', w, f'train_w{w}.json') for w in (1, 2, 4, 8)]
+    runs += [('clip', w, f'train_clip_w{w}.json') for w in (1, 2)] + [('sched', 1, 'train_sched_w1.json')]
+    for variant, world, fname in runs:
+        out = _spawn(_train_worker, world, variant)
         ranks = [json.loads((out / f'rank{r}.json').read_text()) for r in range(world)]
-        meta = {'world': world, 'train_steps': TRAIN_STEPS, 'val_steps': VAL_STEPS, 'epochs': EPOCHS, 'batch': BATCH,
+        meta = {'world': world, 'train_steps': TRAIN_STEPS, 'val_steps': VAL_STEPS,
+                'epochs': EPOCHS + (1 if variant == 'sched' else 0), 'batch': BATCH,
                 'train_seed': '100+rank', 'val_seed': '200+rank', 'init_seed': 0, 'optimizer': 'Adam(lr=1e-3)'}
-        (GOLD / f'train_w{world}.json').write_text(json.dumps({'meta': meta, 'ranks': ranks}))
-        print(f'train_w{world}.json', {k: v[-1] for k, v in ranks[0]['histories'].items() if 'loss' in k})
+        if variant == 'clip':
+            meta['gradient_clip'] = CLIP_NORM
+        if variant == 'sched':
+            meta['scheduler'] = 'StepLR(step_size=1, gamma=0.5)'
+        (GOLD / fname).write_text(json.dumps({'meta': meta, 'ranks': ranks}))
+        print(fname, {k: v[-1] for k, v in ranks[0]['histories'].items() if 'loss' in k})
 
 
 if __name__ == '__main__':

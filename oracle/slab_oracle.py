@@ -220,7 +220,7 @@ class OracleSlab:
         src = self.out_i if is_int else self.out_f
         return torch.from_numpy(src[cell:cell + lanes].copy())
 
-    def export_cells(self, cell, lanes):
+    def export_cells(self, cell, lanes, device_tensors=False):
         bits = np.where([self._is_int(d) for d in self.desc[cell:cell + lanes]], self.acc_i[cell:cell + lanes],
                         self.acc_f[cell:cell + lanes].view(np.int64))
         return torch.from_numpy(bits.astype(np.int64)), torch.from_numpy(self.cnt[cell:cell + lanes].copy())

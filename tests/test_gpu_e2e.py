@@ -33,37 +33,67 @@ def batches(seed, steps, batch):
             for _ in range(steps)]
 
 
-def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0, graph=False, flat_adam=False):
+def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0, graph=False, flat_adam=False,
+                bench_config=False, variant='plain'):
+    """The golden run's script through dmlcloud_b200.  bench_config: exactly what bench.py times — bf16 autocast, bf16
+    gradient wire, whole-step CUDA graph, FlatAdam, cross-rank metric exchange every step, deferred tracker.
+    variant: 'plain' | 'clip' | 'sched' (oracle/gen_golden.py)."""
     from dmlcloud_b200 import TrainValStage
     from dmlcloud_b200.pipeline import TrainingPipeline
 
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    if bench_config:
+        graph, flat_adam, live_every = True, True, 1
 
     class MNISTStage(TrainValStage):
         def pre_stage(self):
             self.pipeline.register_dataset('train', batches(100 + rank, meta['train_steps'], meta['batch']), verbose=False)
             self.pipeline.register_dataset('val', batches(200 + rank, meta['val_steps'], meta['batch']), verbose=False)
             model = make_cnn()
-            self.pipeline.register_model('cnn', model, verbose=False)
+            self.pipeline.register_model('cnn', model, verbose=False, grad_wire='bf16' if bench_config else None)
             if flat_adam:  # libdmlb K5 instead of the torch optimizer the reference run used
                 from dmlcloud_b200.optim import FlatAdam
 
                 optimizer = FlatAdam(model.parameters(), lr=1e-3)
             else:
                 optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph)
-            self.pipeline.register_optimizer('adam', optimizer)
+            scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=1, gamma=0.5) if variant == 'sched' else None
+            self.pipeline.register_optimizer('adam', optimizer, scheduler)
             self.loss = torch.nn.CrossEntropyLoss()
             self.live_metrics_every = live_every
             self.cuda_graph = graph
+            self.tracker.deferred = bench_config
+            self.step_time_counts, self.live_at_epoch_end = [], []
+
+        def gradient_clip(self):
+            return meta.get('gradient_clip', 0.0) if variant == 'clip' else 0.0
 
         def step(self, batch):
             img, target = batch
             img, target = img.to(self.device), target.to(self.device)
-            output = self.pipeline.models['cnn'](img)
+            if bench_config:
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    output = self.pipeline.models['cnn'](img)
+                output = output.float()
+            else:
+                output = self.pipeline.models['cnn'](img)
             loss = self.loss(output, target)
             self.track_reduce('accuracy', (output.argmax(1) == target).float().mean())
             return loss
+
+        def run_epoch(self):
+            self.train_epoch()
+            # every train step's host-measured step time must have reached its cell exactly once — also when it travels
+            # into the captured step through the host feed ring (one replay late, the last one as an immediate)
+            slab = self.tracker._slab
+            slab.flush_all()
+            m = self.tracker.reducers['misc/step_time_ms']
+            self.step_time_counts.append(int(slab.cnt[m.cell].item()))
+            if self.live_metrics:
+                self.live_at_epoch_end.append({k: self.live_metrics[k].value() for k in
+                                               ('train/loss', 'train/accuracy', 'misc/total_train_batches')})
+            self.val_epoch()
 
     p = TrainingPipeline(name='parity')
     p.grad_route, p.metric_route = grad_route, metric_route
@@ -71,10 +101,18 @@ def run_product(rank, meta, grad_route='auto', metric_route='auto', live_every=0
     p.append_stage(stage, max_epochs=meta['epochs'])
     p.run()
     params = torch.cat([q.detach().flatten() for q in p.models['cnn'].parameters()]).double()
+    assert stage.step_time_counts == [meta['train_steps']] * meta['epochs'], stage.step_time_counts
     return p, stage, float(params.sum()), float(params.abs().sum())
 
 
-def compare(p, stage, psum, pabs, ref):
+# Tolerances (stated here and in DESIGN.md §3 "Numerics"):
+#   fp32 runs       losses / accuracies rtol 2e-3, atol 1e-4; parameter sums 1e-3 — cuDNN fp32 convolutions against the
+#                   CPU's MKL-DNN over 12 Adam steps (SURVEY §8d's 1e-5 applies to the metric REDUCTION, which is tested
+#                   bit-exactly against the oracle; these runs also contain the user's model)
+#   bench config    bf16 autocast forward/backward + bf16 gradient wire against the reference's fp32 CPU run: losses
+#                   rtol 2e-2, accuracies atol 4e-2 (an argmax flip moves a 192-sample mean by 5e-3), parameter sums 2e-2
+#   always          integer counters, epochs, metric names and history lengths: bit-exact
+def compare(p, stage, psum, pabs, ref, loose=False):
     assert p.tracker.epoch == ref['tracker_epoch'] and stage.current_epoch == ref['stage_epoch']
     hist = p.tracker.histories
     assert set(hist) == set(ref['histories'])
@@ -92,10 +130,23 @@ def compare(p, stage, psum, pabs, ref):
                 assert str(got.dtype) == str(want.dtype) and got.shape == want.shape, name
                 if np.issubdtype(want.dtype, np.integer):
                     assert (got == want).all(), name  # step / batch counters: bit-exact
+                elif loose:
+                    np.testing.assert_allclose(got, want, rtol=2e-2, atol=4e-2 if 'accuracy' in name else 1e-3, err_msg=name)
                 else:
                     np.testing.assert_allclose(got, want, rtol=2e-3, atol=1e-4, err_msg=name)
-    np.testing.assert_allclose(psum, ref['param_sum'], rtol=1e-3, atol=1e-3)
-    np.testing.assert_allclose(pabs, ref['param_abs_sum'], rtol=1e-3)
+    tol = 2e-2 if loose else 1e-3
+    np.testing.assert_allclose(psum, ref['param_sum'], rtol=tol, atol=tol)
+    np.testing.assert_allclose(pabs, ref['param_abs_sum'], rtol=tol)
+
+
+def check_live_equals_history(p, stage):
+    """The last step's live exchange (running value of the epoch so far, from the fused step exchange's result ring) covers
+    exactly the values the epoch-closing reduce covers: same cells, same finalise, same rank-ordered combine -> every bit."""
+    assert len(stage.live_at_epoch_end) == stage.current_epoch - 1
+    for epoch, live in enumerate(stage.live_at_epoch_end):
+        for name, value in live.items():
+            want = p.tracker.histories[name][epoch]
+            assert value is not None and torch.equal(value, want), (epoch, name, value, want)
 
 
 def test_train_w1_matches_reference_run():
@@ -153,7 +204,92 @@ def test_train_w1_flat_adam_matches_reference_run(graph):
         deinitialize_torch_distributed()
 
 
-def _train_worker(rank, world, initfile, outdir, grad_route, metric_route, graph=False):
+def _w1(fn):
+    from dmlcloud_b200.util.distributed import deinitialize_torch_distributed, init_process_group_dummy
+
+    init_process_group_dummy()
+    try:
+        return fn()
+    finally:
+        deinitialize_torch_distributed()
+
+
+def test_train_w1_bench_configuration_matches_reference_run():
+    """the EXACT configuration bench.py times — bf16 autocast, bf16 wire, captured step with the fused
+    step exchange (live metrics every step), FlatAdam, deferred tracker — against the reference's run."""
+    from dmlcloud_b200 import _native as N
+
+    gold = load_json('train_w1.json')
+    steps = gold['meta']['train_steps'] * gold['meta']['epochs']
+
+    def body():
+        before = N.launch_count()
+        p, stage, psum, pabs = run_product(0, gold['meta'], bench_config=True)
+        compare(p, stage, psum, pabs, gold['ranks'][0], loose=True)
+        check_live_equals_history(p, stage)
+        g = stage._graph
+        assert g is not None and g.replays == steps - 3 and g.step_metrics is not None and g.feed is not None
+        # the captured step launches THREE libdmlb kernels: the fused step exchange (all-reduce + folds + metric exchange),
+        # the K5 optimizer step — and nothing per step outside the graph
+        assert g.kernels_in_graph == 2, g.kernels_in_graph
+        eager = 3 * (1 + 1 + 6 + 1)  # 3 warm-up steps: bucket launch, fold launch, 6 per-parameter K5, live exchange
+        assert N.launch_count() - before < eager + 2 * gold['meta']['epochs'] * 4 + 40
+        assert p.optimizers['adam'].steps_taken() == steps
+
+    _w1(body)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_train_w1_gradient_clipping_matches_reference_run(graph):
+    """reference stage.py:276-285 with gradient_clip() != 0, through the stage: eager = the all-reduce's fused sum of
+    squares + one scale pass (no extra read of the gradients); captured = coefficient applied inside the K5 launch."""
+    from dmlcloud_b200 import _native as N
+
+    gold = load_json('train_clip_w1.json')
+
+    def body():
+        before = N.launch_count()
+        p, stage, psum, pabs = run_product(0, gold['meta'], graph=graph, flat_adam=graph, variant='clip')
+        compare(p, stage, psum, pabs, gold['ranks'][0])
+        if not graph:
+            sync = p.grad_syncs['cnn']
+            assert sync.sumsq is not None  # the bucket launches accumulated it; no dmlb_bucket_sumsq pass was needed
+            steps = gold['meta']['train_steps'] * gold['meta']['epochs']
+            # per step: the bucket launch(es) of the hook (W = 1, fp32 wire: scale + sum of squares of the ONE bucket), 6 clip
+            # launches (one per parameter tensor), 1 fold — and no per-parameter sum-of-squares pass (6 more launches)
+            assert N.launch_count() - before <= steps * 9 + 40
+
+    _w1(body)
+
+
+def test_train_w1_scheduler_is_followed_by_the_captured_step():
+    """a python-float lr was baked into the captured graph.  FlatAdam keeps lr in device memory: StepLR halves
+    it after every epoch and the replays follow (reference stage.py:316-318)."""
+    gold = load_json('train_sched_w1.json')
+
+    def body():
+        p, stage, psum, pabs = run_product(0, gold['meta'], graph=True, flat_adam=True, variant='sched')
+        compare(p, stage, psum, pabs, gold['ranks'][0])
+        assert [float(v) for v in p.tracker['misc/lr_adam']] == [1e-3, 5e-4, 2.5e-4]
+        opt = p.optimizers['adam']
+        assert float(opt._flat[0]['lr'].item()) == 2.5e-4   # device-resident value the last epoch's replays applied
+        assert opt.param_groups[0]['lr'] == 1.25e-4           # the scheduler's next value, synced before the next replay
+
+    _w1(body)
+
+
+def test_torch_optimizer_with_scheduler_is_refused_in_graph_mode():
+    gold = load_json('train_sched_w1.json')
+
+    def body():
+        with pytest.raises(RuntimeError, match='learning rate is baked'):
+            run_product(0, gold['meta'], graph=True, flat_adam=False, variant='sched')
+
+    _w1(body)
+
+
+def _train_worker(rank, world, initfile, outdir, grad_route, metric_route, graph=False, bench_config=False,
+                  variant='plain'):
     init_gloo(rank, world, initfile)
     import torch.distributed as dist
 
@@ -164,26 +300,44 @@ def _train_worker(rank, world, initfile, outdir, grad_route, metric_route, graph
 
     D._here = D.Placement('test', rank, world, rank_device(rank), world, 0)
     torch.cuda.set_device(rank_device(rank))
-    gold = load_json(f'train_w{world}.json')
-    p, stage, psum, pabs = run_product(rank, gold['meta'], grad_route, metric_route, graph=graph)
-    compare(p, stage, psum, pabs, gold['ranks'][rank])
+    gold = load_json({'plain': f'train_w{world}.json', 'clip': f'train_clip_w{world}.json'}[variant])
+    p, stage, psum, pabs = run_product(rank, gold['meta'], grad_route, metric_route, graph=graph,
+                                       flat_adam=(graph and variant == 'clip'), bench_config=bench_config, variant=variant)
+    compare(p, stage, psum, pabs, gold['ranks'][rank], loose=bench_config)
+    if bench_config:
+        check_live_equals_history(p, stage)
+        assert stage._graph.kernels_in_graph == 2
     routes = set(p.grad_syncs['cnn'].last_routes.values())
     Path(outdir, f'ok{rank}.json').write_text(json.dumps({'routes': sorted(routes), 'psum': psum}))
     dist.barrier()
     dist.destroy_process_group()
 
 
+def _same_replicas(out, world):
+    res = [json.loads((out / f'ok{r}.json').read_text()) for r in range(world)]
+    assert all(r['psum'] == res[0]['psum'] for r in res)  # replicas stay bit-identical
+    return res
+
+
 def test_train_w2_peer_path_matches_reference_run():
     """W=2 as two processes on one GPU: gradients through the fused peer all-reduce, metrics through the fused slab
     exchange — against the reference's 2-rank gloo run."""
-    out = spawn(_train_worker, 2, 'peer', 'peer', timeout=900)
-    res = [json.loads((out / f'ok{r}.json').read_text()) for r in range(2)]
+    res = _same_replicas(spawn(_train_worker, 2, 'peer', 'peer', timeout=900), 2)
     assert res[0]['routes'] == ['peer'] and res[1]['routes'] == ['peer']
-    assert res[0]['psum'] == res[1]['psum']  # replicas stay bit-identical
 
 
 def test_train_w2_cuda_graph_peer_path_matches_reference_run():
     """W=2 with the captured step: the fused peer all-reduce runs INSIDE the CUDA graph (device-side sequence counter)."""
-    out = spawn(_train_worker, 2, 'peer', 'peer', True, timeout=900)
-    res = [json.loads((out / f'ok{r}.json').read_text()) for r in range(2)]
-    assert res[0]['psum'] == res[1]['psum']
+    _same_replicas(spawn(_train_worker, 2, 'peer', 'peer', True, timeout=900), 2)
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_train_bench_configuration_multi_rank_matches_reference_run(world):
+    """The benched configuration at W = 2, 4, 8 (golden runs of the unmodified reference at the same W): ONE peer barrier
+    per step carries the gradients and the metric records; the live ring equals the epoch histories bit for bit."""
+    _same_replicas(spawn(_train_worker, world, 'peer', 'peer', True, True, timeout=1500), world)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_train_w2_gradient_clipping_matches_reference_run(graph):
+    _same_replicas(spawn(_train_worker, 2, 'peer', 'peer', graph, False, 'clip', timeout=900), 2)
