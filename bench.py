@@ -642,6 +642,16 @@ def kernel_microbench(dev, peaks):
         return N.stream_ptr(torch.cuda.current_stream(dev))
 
     base = statistics.median(graph_time(lambda: flush.zero_()))
+
+    def tiny():
+        flush.zero_()
+        N.check(lib.dmlb_bucket_scale_f32(src.data_ptr(), 4, 1.0, side_ptr()))
+
+    # what ANY kernel node costs in this measurement (node-to-node launch gap + an empty grid's ramp): the floor under the
+    # small buckets.  A 513,000-element bucket moves 3 MB = 0.47 us at the HBM peak; no stand-alone launch can take that
+    # little, which is why the product path fuses the pack into the all-reduce kernel instead of launching it.
+    floor_us = max(statistics.median(graph_time(tiny)) - base, 0.0) * 1e6
+    out['launch_floor_us'] = round(floor_us, 2)
     buckets = []
     for elems in (513_000, 7_213_056, 3_963_456, 11_689_512):
         s = src[:elems]
@@ -654,6 +664,9 @@ def kernel_microbench(dev, peaks):
         secs = [max(t - base, 1e-9) for t in graph_time(body)]
         buckets.append(entry('dmlb_bucket_pack_f32_bf16 (K1)', 6, elems, secs,
                              'cold: 256 MB L2 flush before each launch; graph-captured, flush time subtracted'))
+        net = max(statistics.mean(secs) * 1e6 - floor_us, 1e-3)
+        buckets[-1]['net_of_launch_floor_us'] = round(net, 2)
+        buckets[-1]['frac_net_of_launch_floor'] = round(elems * 6 / (net * 1e-6) / 1e9 / peaks['hbm_gbs'], 4)
         for label, fn in (('regs', lib.dmlb_bucket_pack_f32_bf16_regs), ('tma', lib.dmlb_bucket_pack_f32_bf16_tma)):
             def body_v(fn=fn):
                 flush.zero_()
@@ -699,7 +712,12 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
         xs = sorted(xs)
         return {'median': xs[len(xs) // 2], 'p99': xs[max(0, int(len(xs) * 0.99) - 1)], 'min': xs[0]}
 
-    def variant(kind, iters, warm):
+    def variant(kind, iters, warm, gc_off=False):
+        import gc
+
+        if gc_off:
+            gc.collect()
+            gc.disable()
         t = MetricTracker()
         t.bind(device=dev, comm=pipeline.metric_comm, group=None)
         t.deferred = True
@@ -772,6 +790,8 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
         def worst(k):
             return {s_: round(max(b_[k][s_] for b_ in box), 2) for s_ in ('median', 'p99', 'min')}
 
+        if gc_off:
+            gc.enable()
         out = {'iters': iters}
         out.update(worst('live'))
         out.update({'host_call': worst('host'), 'back_to_back': worst('pipe'), 'device_aligned': worst('dev'),
@@ -780,6 +800,9 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
 
     out = {'n_metrics': n_metrics, 'world': world, 'unit': 'us'}
     out.update(variant('floats_mixed', 200, 20))  # top-level keys keep r1's meaning (python floats, mixed ops)
+    # the p99 of the call-after-a-host-barrier numbers is a HOST stall between the start event and the launch; with the
+    # Python garbage collector off during the loop it shows whether that stall is a gen-1/2 collection
+    out['floats_mixed_gc_disabled'] = variant('floats_mixed', 200, 20, gc_off=True)
     out['device_mean'] = variant('device_mean', 60, 10)
     out['device_mixed_int64'] = variant('device_mixed', 60, 10)
     out['what'] = ('median/p99/min: CUDA-event time of MetricTracker.reduce_live() (fused reduce kernel writing into mapped '

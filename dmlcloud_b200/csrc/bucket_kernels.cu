@@ -197,22 +197,29 @@ __device__ __forceinline__ void prologue(F &) {}
 // in the body, n = total elements.
 template <class F, bool kReduce>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-stream_kernel(F f, size_t head, size_t nvec, size_t n, double *sumsq_out) {
+stream_kernel(F f, size_t head, size_t nvec, size_t n, double *sumsq_out, size_t chunk) {
     prologue(f);
     double part = 0.0;
     constexpr int U = unroll_of<F>::value;
-    const size_t sweep = (size_t)gridDim.x * kThreads * U;
-    for (size_t base = (size_t)blockIdx.x * kThreads * U + threadIdx.x; base < nvec; base += sweep) {
+    // chunk == 0: grid-stride sweeps (large inputs: the whole grid walks one 19 MB window at a time).
+    // chunk  > 0: CTA b owns vectors [b * chunk, (b + 1) * chunk) — DDP-bucket-sized inputs are one or two waves long, and
+    //             with work handed out in fixed 2048-vector blocks some SMs get 4 CTAs' worth and others 3 (a 3.96 M
+    //             element bucket: 484 blocks on 148 SMs).  Equal chunks on a grid that is a multiple of the SM count give
+    //             every SM the same number of bytes.
+    const size_t lo = chunk ? (size_t)blockIdx.x * chunk : (size_t)blockIdx.x * kThreads * U;
+    const size_t hi = chunk ? min(nvec, lo + chunk) : nvec;
+    const size_t sweep = chunk ? (size_t)kThreads * U : (size_t)gridDim.x * kThreads * U;
+    for (size_t base = lo + threadIdx.x; base < hi; base += sweep) {
         typename F::In v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             size_t i = base + (size_t)u * kThreads;
-            if (i < nvec) v[u] = f.ld(i);
+            if (i < hi) v[u] = f.ld(i);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             size_t i = base + (size_t)u * kThreads;
-            if (i < nvec) part += f.st(i, v[u]);
+            if (i < hi) part += f.st(i, v[u]);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < 16) {  // unaligned head (< 4 elems) and ragged tail (< kElems elems)
@@ -262,8 +269,21 @@ static int launch_stream(F f, long head, size_t n, double *sumsq, cudaStream_t s
     }
     size_t h = (size_t)head < n ? (size_t)head : n;
     size_t nvec = (n - h) / elems_of<F>::value;
-    int grid = stream_grid(nvec, unroll_of<F>::value, kCtasPerSm);
-    stream_kernel<F, kReduce><<<grid, kThreads, 0, st>>>(f, h, nvec, n, sumsq);
+    const size_t per_cta = (size_t)kThreads * unroll_of<F>::value;
+    const size_t want = (nvec + per_cta - 1) / per_cta;
+    const size_t sms = (size_t)sm_count(), cap = sms * kCtasPerSm;
+    int grid;
+    size_t chunk = 0;
+    if (want <= 2 * cap) {  // at most two waves: balance the SMs (see stream_kernel)
+        size_t g = want < sms ? (want < 1 ? 1 : want) : ((want + sms - 1) / sms) * sms;
+        if (g > cap) g = cap;
+        grid = (int)g;
+        chunk = (nvec + g - 1) / g;
+        if (chunk < 1) chunk = 1;
+    } else {
+        grid = stream_grid(nvec, unroll_of<F>::value, kCtasPerSm);
+    }
+    stream_kernel<F, kReduce><<<grid, kThreads, 0, st>>>(f, h, nvec, n, sumsq, chunk);
     return launched();
 }
 
