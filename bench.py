@@ -593,7 +593,7 @@ def kernel_microbench(dev, peaks):
     quarters = [src.data_ptr() + 4 * q * i for i in range(4)]
     adam = timed(lambda: N.check(lib.dmlb_adam_step_f32(quarters[0], quarters[1], quarters[2], quarters[3], q, 1e-3, 0.9,
                                                         0.999, 1e-8, 0.0, 0, 0, None, 0.0, adam_state.data_ptr(), 1, None,
-                                                        st)))
+                                                        0, st)))
     traffic = {'pack': ncu_traffic('pack_bf16_tma_kernel'), 'pack_regs': ncu_traffic('PackBf16'),
                'unpack_tma': ncu_traffic('unpack_bf16_tma_kernel'), 'unpack_regs': ncu_traffic('UnpackBf16'),
                'scale': ncu_traffic('ScaleInplace')}
@@ -735,7 +735,7 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
             block = torch.randn(n_metrics, generator=g, device=dev)
             vals = list(block.unbind(0))  # 1024 separate 0-d device tensors (views of one block)
             cvals = list(torch.randint(0, 1000, (len(counters),), generator=g, device=dev).unbind(0))
-        live_us, live_host_us, epoch_us, pipe_us, dev_us = [], [], [], [], []
+        live_us, live_host_us, epoch_us, pipe_us, dev_us, parts = [], [], [], [], [], []
         for it in range(warm + iters):
             for name, v in zip(names, vals):
                 t.track(name, v)
@@ -747,7 +747,9 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             h0 = time.perf_counter()
             a.record()
+            ha = time.perf_counter()
             live = t.reduce_live()
+            hb = time.perf_counter()
             b.record()
             h1 = time.perf_counter()
             b.synchronize()
@@ -755,6 +757,7 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
             if it >= warm:
                 live_us.append(a.elapsed_time(b) * 1e3)
                 live_host_us.append((h1 - h0) * 1e6)
+                parts.append(((ha - h0) * 1e6, (hb - ha) * 1e6, (h1 - hb) * 1e6))
             if it % 10 == 9:
                 R = 10
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -793,6 +796,10 @@ def metric_reduce_microbench(pipeline, dev, world, rank, n_metrics=1024):
         if gc_off:
             gc.enable()
         out = {'iters': iters}
+        # where a slow call spends its HOST time (this rank): the timing event's record, the reduce_live() call, the end event
+        slow = max(range(len(parts)), key=lambda i: sum(parts[i]))
+        out['slowest_call_host_us'] = {'event_record_start': round(parts[slow][0], 1), 'reduce_live': round(parts[slow][1], 1),
+                                       'event_record_end': round(parts[slow][2], 1)}
         out.update(worst('live'))
         out.update({'host_call': worst('host'), 'back_to_back': worst('pipe'), 'device_aligned': worst('dev'),
                     'next_epoch': worst('epoch')})

@@ -74,9 +74,9 @@ SIGNATURES = {
     'dmlb_bucket_clip_f32': (c_int, [c_void_p, c_size_t, c_void_p, c_float, c_void_p]),
     'dmlb_adam_step_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_double, c_double, c_double,
                                    c_double, c_double, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
-                                   c_void_p]),
+                                   c_int, c_void_p]),
     'dmlb_sgd_step_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_double, c_double, c_double, c_double, c_int,
-                                  c_int, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+                                  c_int, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     'dmlb_multi_pack': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_float, c_void_p]),
     'dmlb_multi_unpack': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     'dmlb_ipc_get_handle': (c_int, [c_void_p, c_void_p]),

@@ -68,8 +68,8 @@ __device__ __forceinline__ long long load_as_i64(const void *p, int dtype, size_
 //   steps*k <  32 : one thread per cell, sequential                                        (scalars: lanes = k = 1)
 // Immediates (src == NULL): `imm` is the pre-combined value of `steps` host scalars (the host merges python scalars that
 // hit the same cell between two launches), so acc = op(acc, imm), cnt += steps.
-// Feed entries (src_dtype == DMLB_SRC_FEED): src points at one slot of the mapped host feed ring — DMLB_FEED_WIDTH doubles
-// of pre-combined values followed by DMLB_FEED_WIDTH doubles of counts; entry index = k; count 0 = nothing this step.
+// Feed entries (src_dtype == DMLB_SRC_FEED): src points at one slot of the mapped host feed ring — DMLB_FEED_WIDTH pairs
+// {pre-combined value, count} of doubles; entry index = k; count 0 = nothing this step.
 __device__ __forceinline__ void fold_entry(uint64_t *acc, long long *cnt, const uint32_t *desc, const dmlb_fold_entry &e,
                                            int tid, int nthreads) {
     const uint32_t d = desc[e.cell];
@@ -82,13 +82,11 @@ __device__ __forceinline__ void fold_entry(uint64_t *acc, long long *cnt, const 
             if (e.src == nullptr) {
                 fv = __longlong_as_double((long long)e.imm);
                 iv = (long long)e.imm;
-            } else {
-                const volatile double *slot = reinterpret_cast<const volatile double *>(e.src);
-                n = (long long)slot[DMLB_FEED_WIDTH + e.k];
-                if (n > 0) {
-                    fv = slot[e.k];
-                    iv = (long long)fv;
-                }
+            } else {  // one 16-byte load = one PCIe read: the row interleaves {value, count} pairs
+                const double2 vc = __ldcv(reinterpret_cast<const double2 *>(e.src) + e.k);
+                n = (long long)vc.y;
+                fv = vc.x;
+                iv = (long long)fv;
             }
             if (n > 0) {
                 if (is_int)

@@ -25,7 +25,7 @@ struct AdamArgs {
     double lr, beta1, beta2;                      // for the fp64 bias corrections
     float w1, b2, w2, eps, weight_decay, decay;   // fl32(1 - beta1), fl32(beta2), fl32(1 - beta2), ..., fl32(1 - lr wd)
     float max_norm;
-    int decoupled, maximize, advance;
+    int decoupled, maximize, advance, zero_grad;
     double weight_decay_d;
 };
 
@@ -47,7 +47,7 @@ __device__ __forceinline__ void adam_element(float &p, float g, float &m, float 
 // V = 1: scalar accesses for views that start at an arbitrary element.
 template <int V>
 __global__ void __launch_bounds__(kThreads, 2)
-adam_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__restrict__ exp_avg,
+adam_kernel(float *__restrict__ param, float *__restrict__ grad, float *__restrict__ exp_avg,
             float *__restrict__ exp_avg_sq, size_t n, AdamArgs a, dmlb_adam_state *state, const double *sumsq,
             const double *lr_dev) {
     __shared__ float s_step_size, s_bc2_sqrt, s_coef, s_decay;
@@ -72,7 +72,7 @@ adam_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__
         constexpr int U = 2;
         const size_t nvec = n / 4;
         float4 *p4 = reinterpret_cast<float4 *>(param);
-        const float4 *g4 = reinterpret_cast<const float4 *>(grad);
+        float4 *g4 = reinterpret_cast<float4 *>(grad);
         float4 *m4 = reinterpret_cast<float4 *>(exp_avg);
         float4 *v4 = reinterpret_cast<float4 *>(exp_avg_sq);
         const size_t sweep = (size_t)gridDim.x * kThreads * U;
@@ -92,17 +92,21 @@ adam_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__
                     adam_element(p[u].z, g[u].z, m[u].z, v[u].z, a, coef, step_size, bc2_sqrt);
                     adam_element(p[u].w, g[u].w, m[u].w, v[u].w, a, coef, step_size, bc2_sqrt);
                     p4[i] = p[u], m4[i] = m[u], v4[i] = v[u];
+                    if (a.zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // the next step accumulates into zeros
                 }
             }
         }
         if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // ragged tail (< 4 elements)
             const size_t e = nvec * 4 + threadIdx.x;
             adam_element(param[e], grad[e], exp_avg[e], exp_avg_sq[e], a, coef, step_size, bc2_sqrt);
+            if (a.zero_grad) grad[e] = 0.0f;
         }
     } else {
         const size_t stride = (size_t)gridDim.x * kThreads;
-        for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride)
+        for (size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride) {
             adam_element(param[e], grad[e], exp_avg[e], exp_avg_sq[e], a, coef, step_size, bc2_sqrt);
+            if (a.zero_grad) grad[e] = 0.0f;
+        }
     }
 
     if (a.advance) {  // every CTA has read `step` by the time the last one arrives here
@@ -122,7 +126,7 @@ adam_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__
 struct SgdArgs {
     double lr;
     float momentum, one_minus_damp, weight_decay, max_norm;
-    int nesterov, maximize, advance, has_buf;
+    int nesterov, maximize, advance, has_buf, zero_grad;
 };
 
 __device__ __forceinline__ void sgd_element(float &p, float g, float &buf, const SgdArgs &a, float coef, float lr, bool first) {
@@ -137,7 +141,7 @@ __device__ __forceinline__ void sgd_element(float &p, float g, float &buf, const
 
 template <int V>
 __global__ void __launch_bounds__(kThreads, 2)
-sgd_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__restrict__ mbuf, size_t n, SgdArgs a,
+sgd_kernel(float *__restrict__ param, float *__restrict__ grad, float *__restrict__ mbuf, size_t n, SgdArgs a,
            dmlb_adam_state *state, const double *sumsq, const double *lr_dev) {
     __shared__ float s_lr, s_coef;
     __shared__ int s_first;
@@ -158,7 +162,7 @@ sgd_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__r
         constexpr int U = 2;
         const size_t nvec = n / 4;
         float4 *p4 = reinterpret_cast<float4 *>(param);
-        const float4 *g4 = reinterpret_cast<const float4 *>(grad);
+        float4 *g4 = reinterpret_cast<float4 *>(grad);
         float4 *b4 = reinterpret_cast<float4 *>(mbuf);
         const size_t sweep = (size_t)gridDim.x * kThreads * U;
         for (size_t base = (size_t)blockIdx.x * kThreads * U + threadIdx.x; base < nvec; base += sweep) {
@@ -181,6 +185,7 @@ sgd_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__r
                     sgd_element(p[u].w, g[u].w, b[u].w, a, coef, lr, first);
                     p4[i] = p[u];
                     if (a.has_buf) b4[i] = b[u];
+                    if (a.zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         }
@@ -189,6 +194,7 @@ sgd_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__r
             float b = (a.has_buf && !first) ? mbuf[e] : 0.0f;
             sgd_element(param[e], grad[e], b, a, coef, lr, first);
             if (a.has_buf) mbuf[e] = b;
+            if (a.zero_grad) grad[e] = 0.0f;
         }
     } else {
         const size_t stride = (size_t)gridDim.x * kThreads;
@@ -196,6 +202,7 @@ sgd_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__r
             float b = (a.has_buf && !first) ? mbuf[e] : 0.0f;
             sgd_element(param[e], grad[e], b, a, coef, lr, first);
             if (a.has_buf) mbuf[e] = b;
+            if (a.zero_grad) grad[e] = 0.0f;
         }
     }
     if (a.advance) {
@@ -217,17 +224,17 @@ using namespace dmlb;
 
 extern "C" {
 
-int dmlb_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n, double lr,
+int dmlb_adam_step_f32(float *param, float *grad, float *exp_avg, float *exp_avg_sq, size_t n, double lr,
                        double beta1, double beta2, double eps, double weight_decay, int decoupled, int maximize,
                        const double *sumsq, float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev,
-                       void *stream) {
+                       int zero_grad, void *stream) {
     if (!state || (n && (!param || !grad || !exp_avg || !exp_avg_sq))) return DMLB_EINVAL;
     if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0)) return DMLB_EINVAL;
     if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 3) return DMLB_EALIGN;
     if (((uintptr_t)state) & 7) return DMLB_EALIGN;
     if (n == 0 && !advance) return DMLB_OK;
     AdamArgs a{lr, beta1, beta2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay,
-               (float)(1.0 - lr * weight_decay), max_norm, decoupled != 0, maximize != 0, advance != 0, weight_decay};
+               (float)(1.0 - lr * weight_decay), max_norm, decoupled != 0, maximize != 0, advance != 0, zero_grad != 0, weight_decay};
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0);
     if (vec) {
@@ -240,9 +247,10 @@ int dmlb_adam_step_f32(float *param, const float *grad, float *exp_avg, float *e
     return launched();
 }
 
-int dmlb_sgd_step_f32(float *param, const float *grad, float *momentum_buf, size_t n, double lr, double momentum,
+int dmlb_sgd_step_f32(float *param, float *grad, float *momentum_buf, size_t n, double lr, double momentum,
                       double dampening, double weight_decay, int nesterov, int maximize, const double *sumsq,
-                      float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev, void *stream) {
+                      float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev, int zero_grad,
+                      void *stream) {
     if (!state || (n && (!param || !grad))) return DMLB_EINVAL;
     if (momentum < 0.0 || weight_decay < 0.0) return DMLB_EINVAL;
     if (momentum != 0.0 && !momentum_buf && n) return DMLB_EINVAL;
@@ -251,7 +259,7 @@ int dmlb_sgd_step_f32(float *param, const float *grad, float *momentum_buf, size
     if (((uintptr_t)state) & 7) return DMLB_EALIGN;
     if (n == 0 && !advance) return DMLB_OK;
     SgdArgs a{lr, (float)momentum, (float)(1.0 - dampening), (float)weight_decay, max_norm, nesterov != 0, maximize != 0,
-              advance != 0, momentum != 0.0};
+              advance != 0, momentum != 0.0, zero_grad != 0};
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)momentum_buf) & 15) == 0);
     if (vec) {

@@ -116,6 +116,7 @@ class GraphedTrainStep:
         self.counter = None
         self.replays_at_ring = 0
         self.live_names = {}
+        self.zero_in_optimizer = False
         self._slab_generation = None
         self._keep = None
         self.step_metrics = None
@@ -183,7 +184,8 @@ class GraphedTrainStep:
     def _one_step(self):
         stage = self.stage
         slab = stage.tracker._slab_or_create()
-        self.bucket.flat.zero_()
+        if not self.zero_in_optimizer:
+            self.bucket.flat.zero_()  # (FlatAdam / FlatSGD zero the gradients they consumed inside their own launch)
         if self.clip:
             self.sumsq.zero_()
         slab.batching = True
@@ -252,6 +254,15 @@ class GraphedTrainStep:
         self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.replays_at_ring = self.replays
         torch.cuda.synchronize(self.device)
+        # `optimizer.zero_grad()` of the next step (reference stage.py:300) is fused into the K5 / K6 launch when ONE flat
+        # optimizer owns every gradient of the bucket: one kernel node and one pass over the gradients fewer per step
+        opts = list(stage.optimizers())
+        self.zero_in_optimizer = (len(opts) == 1 and getattr(opts[0], 'device_lr', False) and len(opts[0].param_groups) == 1
+                                  and opts[0]._flat_grad_base(opts[0].param_groups[0], opts[0]._flat[0]) ==
+                                  self.bucket.flat.data_ptr() and opts[0]._flat[0]['total'] == self.bucket.total)
+        if self.zero_in_optimizer:
+            opts[0].zero_grad_in_step = True
+            self.bucket.flat.zero_()  # once, outside the graph: every replay leaves zeros behind
         self.graph = torch.cuda.CUDAGraph()
         # capture on the very stream the warm-up steps ran on: autograd's AccumulateGrad nodes (stashed by DDP at
         # construction) then already live on the capturing stream and no cross-stream edge enters the graph

@@ -257,12 +257,12 @@ class HostFeed:
 
     def commit(self, replay_index):
         """Write what was put since the last commit into the slot replay number `replay_index` (0-based) will read."""
-        row = self.rows[replay_index % self.SLOTS]
-        row[N.FEED_WIDTH:] = 0.0
+        row = self.rows[replay_index % self.SLOTS]  # [{value, count}] * FEED_WIDTH, interleaved (one 16-byte read per column)
+        row[1::2] = 0.0
         for cell, (value, count) in self.pending.items():
             j = self.cols[cell]
-            row[j] = value
-            row[N.FEED_WIDTH + j] = count
+            row[2 * j] = value
+            row[2 * j + 1] = count
         self.pending = {}
 
     def drain(self):

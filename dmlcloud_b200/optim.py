@@ -29,6 +29,7 @@ class _FlatBase(torch.optim.Optimizer):
 
     device_lr = True   # the kernels read lr from device memory: a captured graph follows a scheduler (graphstep.py)
     fused_clip = True  # step(clip=(sumsq, max_norm)) applies clip_grad_norm_'s coefficient inside the update launch
+    zero_grad_in_step = False  # True (set by the captured step): the update launch also zeroes the gradients it consumed
     EXTRA_STATE = ()   # names of the per-element state buffers besides `param`
 
     def add_param_group(self, param_group):
@@ -165,7 +166,8 @@ class FlatAdam(_FlatBase):
                                       float(group['eps']), float(group['weight_decay']),
                                       int(group['decoupled_weight_decay']), int(group['maximize']), sumsq_ptr, max_norm,
                                       flat['state'].data_ptr(), advance,
-                                      flat['lr'].data_ptr() if self._lib_override is None else None, st)
+                                      flat['lr'].data_ptr() if self._lib_override is None else None,
+                                      int(self.zero_grad_in_step), st)
 
     # -- checkpoint: torch.optim.Adam's format -----------------------------------------------------------------------
     def state_dict(self):
@@ -243,7 +245,8 @@ class FlatSGD(_FlatBase):
                                      float(group['momentum']), float(group['dampening']), float(group['weight_decay']),
                                      int(group['nesterov']), int(group['maximize']), sumsq_ptr, max_norm,
                                      flat['state'].data_ptr(), advance,
-                                     flat['lr'].data_ptr() if self._lib_override is None else None, st)
+                                     flat['lr'].data_ptr() if self._lib_override is None else None,
+                                     int(self.zero_grad_in_step), st)
 
     def state_dict(self):
         state, groups, index = {}, [], 0

@@ -124,18 +124,21 @@ typedef struct {
 } dmlb_adam_state;
 /* lr_dev (optional): DEVICE double holding the learning rate; when non-NULL it overrides `lr`, so a CUDA graph that
  * captured this launch follows a scheduler (reference stage.py:316-318 `scheduler.step()`) without re-capture. */
-int dmlb_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n, double lr,
+/* zero_grad != 0: the kernel writes zeros over `grad` after reading it — `optimizer.zero_grad()` of the next step
+ * (reference stage.py:300) fused in, for gradients that accumulate into a flat bucket (the captured step). */
+int dmlb_adam_step_f32(float *param, float *grad, float *exp_avg, float *exp_avg_sq, size_t n, double lr,
                        double beta1, double beta2, double eps, double weight_decay, int decoupled, int maximize,
                        const double *sumsq, float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev,
-                       void *stream);
+                       int zero_grad, void *stream);
 /* K6: torch.optim.SGD step on flat fp32 buffers (ResNet-18 config: SGD + momentum), 16-20 B/elem:
  *   g = coef * grad (clip coefficient as in K5; negated for maximize);  g += wd * p;
  *   momentum != 0:  buf = first ? g : momentum * buf + (1 - dampening) * g;   g = nesterov ? g + momentum * buf : buf
  *   p -= lr * g.     `first` = state->step == 0 (torch initialises the momentum buffer with the first gradient).
  * momentum_buf may be NULL when momentum == 0.  state / advance / lr_dev as for K5. */
-int dmlb_sgd_step_f32(float *param, const float *grad, float *momentum_buf, size_t n, double lr, double momentum,
+int dmlb_sgd_step_f32(float *param, float *grad, float *momentum_buf, size_t n, double lr, double momentum,
                       double dampening, double weight_decay, int nesterov, int maximize, const double *sumsq,
-                      float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev, void *stream);
+                      float max_norm, dmlb_adam_state *state, int advance, const double *lr_dev, int zero_grad,
+                      void *stream);
 
 /* Multi-tensor variants: gather `count` parameter gradients straight into / out of one flat wire buffer (the graph-
  * captured step keeps no DDP Reducer).  `segs` is a DEVICE array of dmlb_seg built once at registration. */
@@ -186,7 +189,7 @@ int dmlb_comm_set_multicast(void *comm, void *mc_base);
  *                written last) | uint64 val[capacity] | uint8 flag[capacity]
  *   ranges: global cell ranges first (n_global_ranges of them; layout identical on all ranks, covered by layout_hash),
  *           rank-local ranges after; at most DMLB_STEP_METRIC_MAX_CELLS global cells.
- *   feed:   device address of a mapped pinned host ring [feed_slots][2 * DMLB_FEED_WIDTH] doubles (values, counts) for
+ *   feed:   device address of a mapped pinned host ring [feed_slots][DMLB_FEED_WIDTH][2] doubles ({value, count} pairs) for
  *           host scalars (e.g. misc/step_time_ms); fold entries with src_dtype == DMLB_SRC_FEED and k = column read slot
  *           (count % feed_slots); their `src` field is ignored.  NULL / 0 when unused.
  *   counter: device uint64, number of exchanges done through this descriptor (the kernel increments it). */

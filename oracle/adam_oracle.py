@@ -60,7 +60,7 @@ class OracleAdamLib:
         return np.ctypeslib.as_array((ctype * n).from_address(ptr))
 
     def dmlb_adam_step_f32(self, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled,
-                           maximize, sumsq, max_norm, state, advance, lr_dev, stream):
+                           maximize, sumsq, max_norm, state, advance, lr_dev, zero_grad, stream):
         import ctypes
 
         self.launches += 1
@@ -74,6 +74,8 @@ class OracleAdamLib:
         p2, m2, v2 = adam_step(p, g, m, v, int(st[0]) + 1, lr=lr, betas=(beta1, beta2), eps=eps, weight_decay=weight_decay,
                                decoupled=bool(decoupled), maximize=bool(maximize), coef=coef, dtype=np.float32)
         p[:], m[:], v[:] = p2, m2, v2
+        if zero_grad:
+            g[:] = 0
         if advance:
             st[0] += 1
         return 0

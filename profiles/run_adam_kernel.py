@@ -44,7 +44,7 @@ def main():
 
     ours = timed(lambda: N.check(lib.dmlb_adam_step_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3,
                                                         0.9, 0.999, 1e-8, 0.0, 0, 0, None, 0.0, state.data_ptr(), 1, None,
-                                                        st)))
+                                                        0, st)))
     q = torch.nn.Parameter(torch.empty(n, dtype=torch.float32, device=dev).normal_())
     q.grad = g
     ref = torch.optim.Adam([q], lr=1e-3, fused=True)

@@ -74,10 +74,10 @@ def test_argument_validation_needs_no_gpu():
     arenas = (ctypes.c_void_p * 1)(None)
     assert lib.dmlb_comm_create(ctypes.byref(comm), 9, 0, arenas, 1024) == N.EINVAL
     assert lib.dmlb_comm_create(ctypes.byref(comm), 1, 0, arenas, 1024) == N.EALIGN
-    # K5: 18 arguments (doubles for the hyper-parameters) marshalled through ctypes; rejected before any CUDA call
+    # K5: 19 arguments (doubles for the hyper-parameters) marshalled through ctypes; rejected before any CUDA call
     a = ctypes.c_void_p(256)
     adam = lambda p, state, beta1, n=16: lib.dmlb_adam_step_f32(p, a, a, a, n, 1e-3, beta1, 0.999, 1e-8, 0.0, 0, 0, None,  # noqa: E731
-                                                                0.0, state, 1, None, None)
+                                                                0.0, state, 1, None, 0, None)
     assert adam(a, None, 0.9) == N.EINVAL          # no state block
     assert adam(None, a, 0.9) == N.EINVAL          # no parameters
     assert adam(a, a, 1.0) == N.EINVAL             # beta1 outside [0, 1)
@@ -85,7 +85,7 @@ def test_argument_validation_needs_no_gpu():
     assert adam(a, ctypes.c_void_p(260), 0.9) == N.EALIGN  # the state block holds an int64
     # K6 and the communicator knobs: rejected before any CUDA call as well
     sgd = lambda p, buf, mom, nest=0: lib.dmlb_sgd_step_f32(p, a, buf, 16, 0.1, mom, 0.0, 0.0, nest, 0, None, 0.0, a, 1,  # noqa: E731
-                                                          None, None)
+                                                          None, 0, None)
     assert sgd(None, a, 0.9) == N.EINVAL
     assert sgd(a, None, 0.9) == N.EINVAL           # momentum without a momentum buffer
     assert sgd(a, a, 0.0, 1) == N.EINVAL           # nesterov needs momentum

@@ -62,12 +62,12 @@ def test_adam_kernel_vs_oracle(n, cfg):
                 N.check(lib.dmlb_adam_step_f32(scratch[0].data_ptr(), g.data_ptr(), scratch[1].data_ptr(),
                                                scratch[2].data_ptr(), n, c['lr'], c['betas'][0], c['betas'][1], c['eps'],
                                                c['weight_decay'], int(c['decoupled']), int(c['maximize']), None, 0.0,
-                                               state.data_ptr(), 0, None, st), 'adam(no advance)')
+                                               state.data_ptr(), 0, None, 0, st), 'adam(no advance)')
                 assert int(state[0].item()) == t - 1
             N.check(lib.dmlb_adam_step_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, c['lr'],
                                            c['betas'][0], c['betas'][1], c['eps'], c['weight_decay'], int(c['decoupled']),
                                            int(c['maximize']), sumsq.data_ptr() if clip is not None else None,
-                                           clip or 0.0, state.data_ptr(), 1, None, st), 'adam')
+                                           clip or 0.0, state.data_ptr(), 1, None, 0, st), 'adam')
             Pd, M, V = adam_oracle.adam_step(Pd, G, M, V, t, lr=c['lr'], betas=c['betas'], eps=c['eps'],
                                              weight_decay=c['weight_decay'], decoupled=c['decoupled'],
                                              maximize=c['maximize'], coef=coef)
@@ -247,10 +247,11 @@ def test_sgd_kernel_vs_oracle(n, cfg):
                                           123.0 if lr_dev else c['lr'], c['momentum'], c['dampening'], c['weight_decay'],
                                           int(c['nesterov']), int(c['maximize']),
                                           sumsq.data_ptr() if clip is not None else None, clip or 0.0, state.data_ptr(), 1,
-                                          lr_t.data_ptr() if lr_dev else None, st), 'sgd')
+                                          lr_t.data_ptr() if lr_dev else None, int(t == 5), st), 'sgd')
             Pd, Bd = adam_oracle.sgd_step(Pd, G, Bd, t == 1, coef=coef, **c)
         torch.cuda.synchronize()
         assert int(state[0].item()) == 5
+        assert float(g.abs().max().item()) == 0.0  # zero_grad was set on the last step: the gradients it consumed are gone
         assert _rel(p.cpu().numpy(), Pd, 1.0) <= 2e-6, (n, cfg, shift, clip)
         if c['momentum']:
             assert _rel(b.cpu().numpy(), Bd, 1.0) <= 2e-6
