@@ -73,12 +73,16 @@ def parse_args():
     ap.add_argument('--optim', choices=['flat', 'torch'], default='flat',
                     help='optimizer of the step: dmlcloud_b200.optim.FlatAdam / FlatSGD (libdmlb K5 / K6, one launch over '
                          'flat buffers, device-resident lr) or the torch optimizer (capturable)')
-    ap.add_argument('--channels-last', action='store_true', help='keep model + images in NHWC (cuDNN bf16 native layout)')
+    ap.add_argument('--channels-last', choices=['auto', 'on', 'off'], default='auto',
+                    help='keep model + images in NHWC, cuDNN\'s native bf16 layout.  auto = on for ResNet-18 (measured 2.05x: '
+                         '12,316 vs 5,992 samples/s at N=1), off for the MNIST CNN (1-channel input; measured 5 %% slower)')
     ap.add_argument('--checkpoint-every-epoch', action='store_true',
                     help='BASELINE config 3: snapshot model/optimizer/tracker state after every window (= epoch)')
     ap.add_argument('--no-micro', action='store_true', help='skip the kernel / metric microbenchmarks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.channels_last = args.channels_last == 'on' or (args.channels_last == 'auto' and args.workload == 'resnet18')
+    return args
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -341,3 +341,48 @@ def test_train_bench_configuration_multi_rank_matches_reference_run(world):
 @pytest.mark.parametrize('graph', [False, True])
 def test_train_w2_gradient_clipping_matches_reference_run(graph):
     _same_replicas(spawn(_train_worker, 2, 'peer', 'peer', graph, False, 'clip', timeout=900), 2)
+
+
+def test_staged_host_batches_give_the_same_run_as_resident_batches():
+    """graphstep._load: large pinned host batches reach the captured step through a copy stream + two staging buffers
+    (the H2D transfer overlaps the previous step).  Same data, resident vs pinned-host: bit-identical parameters."""
+    from dmlcloud_b200 import TrainValStage
+    from dmlcloud_b200.optim import FlatSGD
+    from dmlcloud_b200.pipeline import TrainingPipeline
+
+    def run(pinned):
+        g = torch.Generator().manual_seed(5)
+        data = [(torch.randn(64, 8192, generator=g), torch.randint(0, 10, (64,), generator=g)) for _ in range(12)]  # 2 MB each
+        data = [(x.pin_memory(), y.pin_memory()) if pinned else (x.cuda(), y.cuda()) for x, y in data]
+
+        class S(TrainValStage):
+            def pre_stage(self):
+                torch.manual_seed(0)
+                model = torch.nn.Sequential(torch.nn.Linear(8192, 64), torch.nn.Tanh(), torch.nn.Linear(64, 10))
+                self.pipeline.register_model('m', model, verbose=False)
+                self.pipeline.register_optimizer('sgd', FlatSGD(model.parameters(), lr=0.05, momentum=0.9))
+                self.pipeline.register_dataset('train', data, verbose=False)
+                self.pipeline.register_dataset('val', [], verbose=False)
+                self.cuda_graph = True
+                self.live_metrics_every = 1
+
+            def step(self, batch):
+                x, y = batch
+                return torch.nn.functional.cross_entropy(self.pipeline.models['m'](x.to(self.device)), y.to(self.device))
+
+            def table_columns(self):
+                return [{'name': 'Epoch', 'metric': 'misc/epoch'}, {'name': 'Loss', 'metric': 'train/loss'}]
+
+        p = TrainingPipeline(name='staged')
+        stage = S()
+        p.append_stage(stage, max_epochs=2)
+        p.run()
+        assert stage._graph is not None and bool(stage._graph._staging) == pinned
+        return torch.cat([q.detach().flatten() for q in p.models['m'].parameters()]).cpu(), p.tracker['train/loss']
+
+    def body():
+        a, la = run(False)
+        b, lb = run(True)
+        assert torch.equal(a, b) and all(torch.equal(x, y) for x, y in zip(la, lb))
+
+    _w1(body)
