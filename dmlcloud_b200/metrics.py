@@ -299,6 +299,7 @@ class DeviceSlab:
         self.acc = self.cnt = self.desc = self.out = None
         self._host_pool = []  # ring of pinned result blocks (see _acquire_host)
         self._host_next = 0
+        self._prepared = {}   # prepared argument sets of the per-step reduce (see _reduce_prepared)
         self._wr = None
         self._range_cache = {}
         self._host_mapped = None  # None = not probed yet; False = pinned memory is not device-mapped here (copy path)
@@ -379,7 +380,8 @@ class DeviceSlab:
                 rc = self._lib().dmlb_host_device_pointer(host.data_ptr(), ctypes.byref(out))
                 self._host_mapped = rc == N.OK and bool(out.value)
                 dptr = out.value if self._host_mapped else None
-            slot = {'host': host, 'dptr': dptr, 'event': torch.cuda.Event(), 'pending': None}
+            slot = {'host': host, 'dptr': dptr, 'event': torch.cuda.Event(), 'pending': None,
+                    'status': host.numpy()[:STATUS_BYTES]}
             ring.append(slot)
             return slot
         slot = ring[self._host_next % self.HOST_RING]
@@ -387,7 +389,7 @@ class DeviceSlab:
         old = slot['pending']
         if old is not None and old.host is not None:
             old.get()  # copy the unread result out of the block before it is overwritten (its event is long complete)
-        slot['host'][:STATUS_BYTES].zero_()
+        slot['status'][:] = 0
         return slot
 
     # -- fold --------------------------------------------------------------------------------------------------------
@@ -482,11 +484,15 @@ class DeviceSlab:
             self._range_cache[key] = hit
         return hit
 
-    def reduce(self, global_ranges, local_ranges, layout_hash, reset=True, exchange=True, to_host=True):
+    def reduce(self, global_ranges, local_ranges, layout_hash, reset=True, exchange=True, to_host=True, plan_key=None):
         """Finalise + cross-rank combine.  `global_ranges` are the cells of globally-reduced metrics (identical layout
         on every rank, covered by `layout_hash`, exchanged); `local_ranges` are rank-local metrics (never exchanged,
         may differ between ranks).  Returns a _PendingResult (to_host) or None."""
         self.flush_all()
+        if to_host and plan_key is not None:
+            fast = self._reduce_prepared(plan_key, global_ranges, local_ranges, layout_hash, reset, exchange)
+            if fast is not None:
+                return fast
         lib = self._lib()
         world, rank = self._world_rank()
         if not exchange:
@@ -538,6 +544,50 @@ class DeviceSlab:
             return None
         if base == out_p:  # pinned memory not device-mapped on this platform: one D2H copy instead
             slot['host'].copy_(self.out, non_blocking=True)
+        slot['event'].record()
+        pending = _PendingResult(self, slot['host'], slot['event'], self.capacity)
+        slot['pending'] = pending
+        return pending
+
+    def _reduce_prepared(self, plan_key, global_ranges, local_ranges, layout_hash, reset, exchange):
+        """The per-step hot path of reduce(): the same selection as last time (`plan_key` identifies it), results into
+        mapped host memory, one launch.  Everything that does not change between calls — the range array, the ctypes
+        argument objects for each of the ring's result blocks — is prepared once; a call is then: pick the ring slot,
+        clear its 128 status bytes, one foreign call, one event record.  (The per-call Python around the launch was what
+        `reduce_live()` spent most of its time on: ~50 us in round 1.)  None -> take the general path."""
+        world, _ = self._world_rank()
+        if not exchange:
+            world = 1
+        if world > 1 and self.comm is None:
+            return None
+        key = (plan_key, bool(reset), world, self.generation, self.n_cells)
+        prep = self._prepared.get(key)
+        if prep is not None and (prep['g'] is not global_ranges or prep['l'] is not local_ranges):
+            prep = None  # an id() collision with a plan that has died: prepare again
+        if prep is None:
+            glob = list(global_ranges) if world > 1 else []
+            loc = list(local_ranges) if world > 1 else list(global_ranges) + list(local_ranges)
+            if len(glob) + len(loc) > N.MAX_RANGES or not (glob or loc):
+                return None
+            if len(self._prepared) > 32:
+                self._prepared.clear()
+            arr, n = self._range_array(tuple(glob) + tuple(loc))
+            prep = self._prepared[key] = {'g': global_ranges, 'l': local_ranges, 'arr': arr, 'n': n, 'n_glob': len(glob), 'slots': {},
+                                          'hash': ctypes.c_uint64(layout_hash),
+                                          'comm': self.comm.handle if world > 1 else None}
+        slot = self._acquire_host()
+        if slot['dptr'] is None:
+            return None
+        args = prep['slots'].get(id(slot))
+        if args is None:
+            base, acc_p, cnt_p, desc_p = slot['dptr'], self._ptrs[0], self._ptrs[1], self._ptrs[2]
+            args = prep['slots'][id(slot)] = (
+                prep['comm'], ctypes.c_void_p(acc_p), ctypes.c_void_p(cnt_p), ctypes.c_void_p(desc_p), ctypes.c_int(self.n_cells),
+                prep['arr'], ctypes.c_int(prep['n']), ctypes.c_int(prep['n_glob']), prep['hash'], ctypes.c_int(int(reset)),
+                ctypes.c_void_p(base + STATUS_BYTES), ctypes.c_void_p(base + STATUS_BYTES + 8 * self.capacity), ctypes.c_void_p(base))
+        rc = self._lib().dmlb_metric_reduce(*args, N.stream_ptr())
+        if rc:
+            N.check(rc, 'metric_reduce')
         slot['event'].record()
         pending = _PendingResult(self, slot['host'], slot['event'], self.capacity)
         slot['pending'] = pending
@@ -929,6 +979,8 @@ class MetricTracker:
         self._version = 0      # bumped whenever the set of reducible cells can have changed
         self._layout_version = 0  # bumped when metrics are registered / bound to cells / restored (not by reduces)
         self._reduce_cache = {}   # prefix -> cached selection + plan of reduce_all (see _reduce_all_fast)
+        self._live_full = {}      # prefix -> (layout version, {name: metric}, plan) of a live exchange over everything
+        self._reduced_this_epoch = False  # True once reduce_all() has given some metric its value for this epoch
         self._live_plan = None  # (version, prefix, epoch) -> cached selection of reduce_live
 
     # -- wiring ------------------------------------------------------------------------------------------------------
@@ -1088,14 +1140,16 @@ class MetricTracker:
         return self._ranges(glob), self._ranges(loc), _layout_hash([m.layout_item() for m in glob])
 
     def _launch(self, bound, reset, plan=None):
-        """One reduce launch for the bound (cell-owning) metrics."""
+        """One reduce launch for the bound (cell-owning) metrics.  A cached plan (the same tuple object every call) lets
+        the slab reuse its prepared launch arguments."""
         slab = self._slab_or_create()
         g, l, layout = plan if plan is not None else self._plan(bound)
-        return slab.reduce(g, l, layout, reset=reset, exchange=True)
+        return slab.reduce(g, l, layout, reset=reset, exchange=True, plan_key=id(plan) if plan is not None else None)
 
     def reduce_all(self, prefix=None, strict=True):
         """Reduces all metrics and appends their reduced values to the history (reference metrics.py:249-273).
         One kernel launch + one small D2H copy for ALL selected metrics, instead of three collectives per metric."""
+        self._reduced_this_epoch = True
         if self._reduce_all_fast(prefix):
             return
         plain, reduced = self._select(prefix, strict)
@@ -1185,10 +1239,21 @@ class MetricTracker:
         unchanged, so the per-step host cost does not grow with #metrics."""
         key = (self._version, prefix, self.epoch)
         if self._live_plan is None or self._live_plan[0] != key:
-            metrics = [m for name, m in self.reducers.items()
-                       if (prefix is None or name.startswith(prefix)) and m.cell is not None
-                       and not self.has_value(name)]
-            self._live_plan = (key, {m.name: m for m in metrics}, self._plan(metrics) if metrics else None)
+            # right after an epoch boundary nothing has a value yet: the selection is "every bound reduced metric", which
+            # only changes with the metric set (`_layout_version`), not with the epoch — no O(#metrics) planning per epoch
+            full = self._live_full.get(prefix)
+            fresh = full is not None and full[0] == self._layout_version and not self._reduced_this_epoch
+            if fresh:
+                self._live_plan = (key, full[1], full[2])
+            else:
+                metrics = [m for name, m in self.reducers.items()
+                           if (prefix is None or name.startswith(prefix)) and m.cell is not None
+                           and not self.has_value(name)]
+                self._live_plan = (key, {m.name: m for m in metrics}, self._plan(metrics) if metrics else None)
+                if not self._reduced_this_epoch:
+                    if len(self._live_full) > 16:
+                        self._live_full.clear()
+                    self._live_full[prefix] = (self._layout_version, self._live_plan[1], self._live_plan[2])
         return self._live_plan[1], self._live_plan[2]
 
     def live_view(self, pending, by_name):
@@ -1199,6 +1264,7 @@ class MetricTracker:
         """Reduces all metrics (if not already reduced) and advances the epoch counter (reference 275-280)."""
         self.reduce_all(strict=False)
         self.epoch += 1
+        self._reduced_this_epoch = False
 
     # -- checkpoint (reference 282-296) ------------------------------------------------------------------------------
     def state_dict(self, device_tensors=False):
@@ -1217,6 +1283,7 @@ class MetricTracker:
         self._version += 1
         self._layout_version += 1
         self._reduce_cache = {}
+        self._live_full = {}
         self._live_plan = None
         self.reducers = {}
         for name, reducer_state in state['reducers'].items():
