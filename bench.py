@@ -332,10 +332,10 @@ def native_arm(args):
             self._window('value' if e % 2 == 1 else 'e2e')  # windows alternate so that drift hits both arms alike
             pairs = len(self.windows['e2e'])
             if e % 2 == 0:
-                if self.target is None:
-                    per_pair = all_max(self.windows['value'][0] + self.windows['e2e'][0]) * 1e-3 / 2  # seconds per window
-                    self.target = int(min(args.max_windows, max(5, -(-args.min_seconds // max(per_pair, 1e-6)))))
-                if pairs >= self.target:
+                if self.target is None and pairs >= 3:  # (median of three: one slow first window must not shorten the run)
+                    per_window = all_max(statistics.median(self.windows['value'] + self.windows['e2e'])) * 1e-3  # seconds
+                    self.target = int(min(args.max_windows, max(5, -(-args.min_seconds // max(per_window, 1e-6)))))
+                if self.target is not None and pairs >= self.target:
                     v = statistics.median(self.windows['value'])
                     x = statistics.median(self.windows['e2e'])
                     # e2e does strictly more work than value: if it measures faster by > 2 % the windows are still too
