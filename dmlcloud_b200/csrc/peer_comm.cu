@@ -353,11 +353,13 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
 // ---------------------------------------------------------------------------------------------------------------------
 // two-shot: slice q (S wire vectors) is reduced by rank q.  CTA b owns vector range [b*per, (b+1)*per) of EVERY slice,
 // so it only ever depends on what the peers' CTA b wrote (per-CTA barriers suffice).
-// kNvls: the reduce-scatter + all-gather pair is done by the switch — multimem.ld_reduce of my slice from the multicast
+// kNvls = 1: the reduce-scatter + all-gather pair is done by the switch — multimem.ld_reduce of my slice from the multicast
 // mapping of all staging halves, multimem.st of the sum back into every rank's staging half (in place: between the two
 // barriers only the owner touches slice q), then every rank widens its own, now reduced, staging half.
+// kNvls = 2: only the reduce-scatter goes through the switch (one request stream per GPU instead of W-1); the reduced slices
+// stay in their owner's result half and the all-gather is the peer-load phase of the plain two-shot, fused with K2.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kWire, int kU, bool kNvls>
+template <int kWire, int kU, int kNvls>
 __global__ void __launch_bounds__(kCommThreads, 2)
 allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t nvec, size_t S, float scale,
                          double *sumsq_out, int n_data, const __grid_constant__ dmlb_step_metrics M) {
@@ -391,6 +393,7 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
         if (ok && lo < lim) {
             if (kNvls) {
                 unsigned char *mcs = c.mc_stage(half) + off * 16;
+                uint4 *res = reinterpret_cast<uint4 *>(c.result(c.rank, half));
                 constexpr int kV = 4;  // independent in-switch reductions in flight per thread
                 for (size_t i0 = lo + threadIdx.x; i0 < lim; i0 += (size_t)kCommThreads * kV) {
                     uint4 v[kV];
@@ -402,7 +405,10 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
 #pragma unroll
                     for (int u = 0; u < kV; ++u) {
                         const size_t i = i0 + (size_t)u * kCommThreads;
-                        if (i < lim) mc_store(mcs + i * 16, v[u]);
+                        if (i < lim) {
+                            if (kNvls == 1) mc_store(mcs + i * 16, v[u]);  // broadcast by the switch into every staging half
+                            else res[i] = v[u];                            // kept local: the peers pull it in phase 3
+                        }
                     }
                 }
             } else {
@@ -423,8 +429,8 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
 #pragma unroll
             for (int q = 0; q < kMaxW; ++q)
                 if (q < c.world && (size_t)q * S + i < nvec)
-                    w[q] = kNvls ? ld_coherent_u4(reinterpret_cast<const uint4 *>(mine) + (size_t)q * S + i)
-                                 : ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
+                    w[q] = kNvls == 1 ? ld_coherent_u4(reinterpret_cast<const uint4 *>(mine) + (size_t)q * S + i)
+                                      : ld_coherent_u4(reinterpret_cast<const uint4 *>(c.result(q, half)) + i);
 #pragma unroll
             for (int q = 0; q < kMaxW; ++q) {
                 const size_t g = (size_t)q * S + i;
@@ -552,8 +558,9 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
     }
     cudaStream_t st = (cudaStream_t)stream;
     const bool nvls = W > 1 && c->dev.mc != nullptr &&
-                      (algo == 3 || (algo == 0 && W >= kNvlsMinWorld && bytes >= kNvlsMinBytes));
-    if (algo == 3 && !nvls && W > 1) return DMLB_ESTATE;
+                      (algo == 3 || algo == 4 || (algo == 0 && W >= kNvlsMinWorld && bytes >= kNvlsMinBytes));
+    if ((algo == 3 || algo == 4) && !nvls && W > 1) return DMLB_ESTATE;
+    const bool nvls_rs_only = nvls && algo == 4;
     const bool oneshot = !nvls && (W == 1 || algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || W <= 2)));
     const int kU = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
     const size_t items = oneshot ? nvec : (nvec + W - 1) / W;  // vectors a CTA grid is spread over
@@ -569,12 +576,15 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
         if (oneshot)                                                                                                     \
             allreduce_oneshot_kernel<WIRE, U><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, scale, sumsq,      \
                                                                              n_data, M);                                 \
+        else if (nvls_rs_only)                                                                                           \
+            allreduce_twoshot_kernel<WIRE, U, 2><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items, scale,   \
+                                                                                sumsq, n_data, M);                       \
         else if (nvls)                                                                                                   \
-            allreduce_twoshot_kernel<WIRE, U, true><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,       \
-                                                                                   scale, sumsq, n_data, M);             \
+            allreduce_twoshot_kernel<WIRE, U, 1><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items, scale,   \
+                                                                                sumsq, n_data, M);                       \
         else                                                                                                             \
-            allreduce_twoshot_kernel<WIRE, U, false><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items,      \
-                                                                                    scale, sumsq, n_data, M);            \
+            allreduce_twoshot_kernel<WIRE, U, 0><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, nvec, items, scale,   \
+                                                                                sumsq, n_data, M);                       \
     } while (0)
     if (wire == DMLB_WIRE_BF16) {
         if (kU == 4) DMLB_LAUNCH_AR(DMLB_WIRE_BF16, 4);

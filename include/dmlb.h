@@ -198,7 +198,8 @@ typedef struct dmlb_step_metrics dmlb_step_metrics; /* defined below, after the 
 /* in-place averaged all-reduce of an fp32 bucket: bucket = sum_r wire(bucket_r * scale)  (scale = 1/W).
  * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot (reduce-scatter + all-gather through
  * peer loads), 3 NVLS (in-switch reduction: multimem.ld_reduce of this rank's slice + multimem.st of the sum; needs
- * dmlb_comm_set_multicast; the switch's summation order replaces the rank order, see DESIGN.md numerics).
+ * dmlb_comm_set_multicast; the switch's summation order replaces the rank order, see DESIGN.md numerics), 4 NVLS for the
+ * reduce-scatter half only (the reduced slices are all-gathered with peer loads, fused with the write-back).
  * metrics (optional, host struct copied by value): the fused step exchange above.  n may be 0 with metrics != NULL
  * (metric-only step).  With world == 1 the same kernel runs without staging or barrier (bucket rounded through the wire
  * dtype in place), so numerics and launch structure do not depend on W. */

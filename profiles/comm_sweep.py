@@ -98,6 +98,7 @@ def main():
             one_us = time_algo(1) if big else None                          # one-shot forced
             pull_us = time_algo(2) if big else None                         # two-shot (peer loads) forced
             nvls_us = time_algo(3) if big and sync.comm.multicast else None  # in-switch reduction forced
+            nvls_rs_us = time_algo(4) if big and sync.comm.multicast else None  # in-switch reduce-scatter + peer-load all-gather
             # ---- NCCL route ----
             buf2 = base.clone()
             stage = torch.empty(n, dtype=torch.bfloat16, device=dev) if wire == 'bf16' else None
@@ -139,6 +140,7 @@ def main():
                             'oneshot_forced': entry(one_us) if one_us else None,
                             'twoshot_forced': entry(pull_us) if pull_us else None,
                             'nvls_forced': entry(nvls_us) if nvls_us else None,
+                            'nvls_reduce_scatter_plus_pull_forced': entry(nvls_rs_us) if nvls_rs_us else None,
                             'rel_diff_nvls_vs_nccl': nvls_diff,
                             'nccl_route_k1_allreduce_k2': entry(nccl_us),
                             'speedup_vs_nccl_route': round(nccl_us / fused_us, 2), 'rel_diff_fused_vs_nccl': diff})

@@ -114,6 +114,9 @@ def _allreduce_worker(rank, world, initfile, outdir, cases):
                                           for r in range(world)]) for s in range(2)])
             reduced = None
         sync = syncs[wire]
+        if algo in (3, 4) and not sync.comm.multicast:
+            results[f'{name}/skipped'] = {'bit_exact_vs_oracle': True, 'max_abs_vs_oracle': 0.0, 'sumsq_rel': 0.0}
+            continue
         for s in range(locals_.shape[0]):
             buf = torch.from_numpy(locals_[s, rank].copy()).cuda()
             sync.zero_sumsq()
@@ -125,7 +128,7 @@ def _allreduce_worker(rank, world, initfile, outdir, cases):
                                                 sync.sumsq.data_ptr(), algo, None, N.stream_ptr()), 'allreduce')
             torch.cuda.synchronize()
             got = buf.cpu().numpy()
-            twoshot = algo == 2 or (algo == 0 and world > 2 and buf.numel() * (2 if wire == 'bf16' else 4) > 512 * 1024)
+            twoshot = algo in (2, 3, 4) or (algo == 0 and world > 2 and buf.numel() * (2 if wire == 'bf16' else 4) > 512 * 1024)
             want = grad_oracle.allreduce_f32(locals_[s]) if wire == 'fp32' else \
                 grad_oracle.allreduce_bf16(locals_[s], round_result=twoshot)
             key = f'{name}/{s}'
@@ -151,6 +154,8 @@ def _check(world, cases, tol):
     res = [json.loads((out / f'res{r}.json').read_text()) for r in range(world)]
     for key in res[0]:
         name = key.split('/')[0]
+        if key.endswith('/skipped'):
+            continue
         for r in range(world):
             e = res[r][key]
             assert e['bit_exact_vs_oracle'], (key, r, e)  # rank-ordered fp32 sum == oracle, every bit
@@ -203,6 +208,21 @@ def test_fused_allreduce_odd_and_full_world(world):
             cases += [(f'{wire}:n{n}a2', wire, 2, str(n)), (f'{wire}:n{n}a1', wire, 1, str(n)),
                       (f'{wire}:n{n}a2b', wire, 2, str(n)), (f'{wire}:n{n}a0', wire, 0, str(n))]
     _check(world, cases, TOL)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='NVSwitch multicast needs one GPU per rank')
+def test_nvls_allreduce_two_gpus():
+    """algo 3 (multimem.ld_reduce + multimem.st) and algo 4 (in-switch reduce-scatter + peer-load all-gather) on arenas
+    bound to an NVSwitch multicast object.  At W = 2 a sum of two terms has no order, so the in-switch result must equal
+    the rank-ordered oracle bit for bit (bf16 wire: sum rounded to bf16, like the two-shot path)."""
+    cases = []
+    for n in (9, 4097, 600_001, 3_963_456):
+        for wire in ('fp32', 'bf16'):
+            if n * (4 if wire == 'fp32' else 2) > (8 << 20):
+                continue  # (the test communicator's arena takes 8 MB messages)
+            for algo in (3, 4, 2, 3):
+                cases.append((f'{wire}:n{n}a{algo}x{len(cases)}', wire, algo, str(n)))
+    _check(2, cases, TOL)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
