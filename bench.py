@@ -242,6 +242,7 @@ def native_arm(args):
             self.cuda_graph = use_graph
             self.cuda_graph_warmup = eager_steps
             self.live_metrics_every = 1  # metrics cross ranks EVERY step (BASELINE configs 2/3)
+            self.manual_gc = True        # Python's cyclic GC runs at epoch boundaries, not inside a step (stage.py)
             self.tracker.deferred = True
             self.host = gen_batches(100 + rank, max(W, K), pinned=True)
             self.resident = [(x.to(dev), y.to(dev)) for x, y in self.host]
@@ -460,6 +461,7 @@ def native_arm(args):
                    'grad_route': sorted(set(sync.last_routes.values())) if graph is None else
                    ['single' if world == 1 else 'peer'],
                    'multicast': bool(sync.comm is not None and sync.comm.multicast),
+                   'python_gc': 'cyclic collector runs at epoch (= window) boundaries, not inside the step loop (stage.manual_gc)',
                    'metric_route': 'peer' if (pipeline.metric_comm is not None or graph is not None) else
                    ('single' if world == 1 else 'collective'),
                    'timing': f'median of {len(value_windows)} windows of {K} steps per arm (value / e2e alternating), each '

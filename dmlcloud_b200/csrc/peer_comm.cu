@@ -191,7 +191,10 @@ __device__ __forceinline__ void reduce_range(const CommDev &c, int half, size_t 
 // ---------------------------------------------------------------------------------------------------------------------
 // The metric CTA of the fused step exchange (block index == number of data CTAs).
 // fold -> finalise (no reset) -> records into mstage[half] -> the collective's barrier 0 -> rank-ordered combine -> ring.
+// kLL: the records travel as LL lines pushed into every rank's arena (header = lines 0,1; record i = lines 2+2i, 3+2i),
+// so the exchange costs one one-way NVLink latency: no barrier, no peer loads (the LL all-reduce kernel's companion).
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool kLL>
 __device__ __noinline__ void metric_cta(const CommDev &c, uint32_t s, const dmlb_step_metrics &M) {
     __shared__ unsigned long long s_count;
     long long *cnt = reinterpret_cast<long long *>(M.cnt);
@@ -245,7 +248,15 @@ __device__ __noinline__ void metric_cta(const CommDev &c, uint32_t s, const dmlb
         uint64_t val;
         long long n;
         finalize_cell(M.acc, cnt, M.desc[cell], cell, val, n, false);
-        if (exchange) {
+        if (exchange && kLL) {
+#pragma unroll
+            for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+                if (r < c.world) {
+                    uint4 *dst = c.ll_metric(r, half, c.rank) + 2 + 2 * i;
+                    ll_store(dst, (uint32_t)val, (uint32_t)(val >> 32), s);
+                    ll_store(dst + 1, (uint32_t)(uint64_t)n, (uint32_t)((uint64_t)n >> 32), s);
+                }
+        } else if (exchange) {
             rec_mine[2 + 2 * i] = val;
             rec_mine[3 + 2 * i] = (uint64_t)n;
         } else {
@@ -254,7 +265,49 @@ __device__ __noinline__ void metric_cta(const CommDev &c, uint32_t s, const dmlb
         }
     }
     int st = DMLB_METRIC_OK;
-    if (exchange) {
+    if (exchange && kLL) {
+        if (threadIdx.x < c.world) {  // header lines to rank threadIdx.x
+            uint4 *dst = c.ll_metric(threadIdx.x, half, c.rank);
+            ll_store(dst, (uint32_t)M.layout_hash, (uint32_t)(M.layout_hash >> 32), s);
+            ll_store(dst + 1, (uint32_t)n_glob, 0u, s);
+        }
+        // 3. every rank's header has to arrive and agree before any record index is trusted
+        uint4 w[DMLB_MAX_WORLD];
+        bool arrived = true;
+        if (threadIdx.x == 0) {
+            arrived = ll_wait_all(c, s, [&](int r) { return c.ll_metric(c.rank, half, r); }, w);
+            if (arrived) {
+                for (int r = 0; r < c.world; ++r)
+                    if ((((uint64_t)w[r].z << 32) | w[r].x) != M.layout_hash) st = DMLB_METRIC_LAYOUT;
+                arrived = ll_wait_all(c, s, [&](int r) { return c.ll_metric(c.rank, half, r) + 1; }, w);
+                for (int r = 0; arrived && r < c.world; ++r)
+                    if (w[r].x != (uint32_t)n_glob) st = DMLB_METRIC_LAYOUT;
+            }
+            if (!arrived) st = DMLB_METRIC_TIMEOUT;
+        }
+        const bool ok = __syncthreads_or(st != DMLB_METRIC_OK) == 0;
+        // 4. combine in rank order (each thread polls the lines of its own cells)
+        if (ok)
+            for (int i = threadIdx.x; i < n_glob; i += kCommThreads) {
+                const int cell = sel_to_cell(M.ranges, M.n_global_ranges, i);
+                uint4 wv[DMLB_MAX_WORLD], wn[DMLB_MAX_WORLD];
+                const bool got = ll_wait_all(c, s, [&](int r) { return c.ll_metric(c.rank, half, r) + 2 + 2 * i; }, wv) &&
+                                 ll_wait_all(c, s, [&](int r) { return c.ll_metric(c.rank, half, r) + 3 + 2 * i; }, wn);
+                if (!got) {
+                    st = DMLB_METRIC_TIMEOUT;
+                    break;
+                }
+                uint64_t out;
+                uint8_t flag;
+                auto rec = [&](int r, uint64_t &v, long long &n) {
+                    v = ((uint64_t)wv[r].z << 32) | wv[r].x;
+                    n = (long long)(((uint64_t)wn[r].z << 32) | wn[r].x);
+                };
+                combine_cell(M.desc[cell], c.world, rec, out, flag, st);
+                out_val[cell] = out;
+                out_flag[cell] = flag;
+            }
+    } else if (exchange) {
         if (threadIdx.x == 0) {
             rec_mine[0] = M.layout_hash;
             rec_mine[1] = (uint64_t)n_glob;
@@ -309,7 +362,7 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     constexpr int E = W::kElems;
     const uint32_t s = comm_begin(c);
     if ((int)blockIdx.x >= n_data) {
-        metric_cta(c, s, M);
+        metric_cta<false>(c, s, M);
         comm_end(c, s);
         return;
     }
@@ -351,6 +404,86 @@ allreduce_oneshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// one-shot, LL protocol (messages up to kLLMaxPayload wire bytes, W > 1): see peer_comm.cuh.  A line carries 8 payload bytes
+// = 4 bf16 or 2 fp32 elements.  Every thread pushes its lines to all W ranks (its own included: the pull loop is uniform),
+// then polls its own arena's lines of the same indices from all W sources and sums in rank order — bit-identical to the
+// barrier one-shot and to the oracle.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int kWire>
+__global__ void __launch_bounds__(kCommThreads, 2)
+allreduce_ll_kernel(const __grid_constant__ CommDev c, float *bucket, size_t n, size_t n_lines, float scale,
+                    double *sumsq_out, int n_data, const __grid_constant__ dmlb_step_metrics M) {
+    constexpr int EL = kWire == DMLB_WIRE_BF16 ? 4 : 2;  // elements per line
+    const uint32_t s = comm_begin(c);
+    if ((int)blockIdx.x >= n_data) {
+        metric_cta<true>(c, s, M);
+        comm_end(c, s);
+        return;
+    }
+    const int half = s & 1;
+    const size_t per = (n_lines + n_data - 1) / n_data;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = min(n_lines, lo + per);
+    // push
+    for (size_t l = lo + threadIdx.x; l < hi; l += kCommThreads) {
+        float v[EL];
+        const size_t e0 = l * EL;
+#pragma unroll
+        for (int j = 0; j < EL; ++j) v[j] = (e0 + j < n) ? bucket[e0 + j] * scale : 0.0f;
+        uint32_t d0, d1;
+        if (kWire == DMLB_WIRE_BF16) {
+            d0 = pack_bf16x2(v[0], v[1]);
+            d1 = pack_bf16x2(v[EL - 2], v[EL - 1]);
+        } else {
+            d0 = __float_as_uint(v[0]);
+            d1 = __float_as_uint(v[1]);
+        }
+#pragma unroll
+        for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+            if (r < c.world) ll_store(c.ll(r, half, c.rank) + l, d0, d1, s);
+    }
+    // pull + sum in rank order
+    double part = 0.0;
+    const bool want_sumsq = sumsq_out != nullptr;
+    bool ok = true;
+    for (size_t l = lo + threadIdx.x; l < hi && ok; l += kCommThreads) {
+        uint4 w[DMLB_MAX_WORLD];
+        ok = ll_wait_all(c, s, [&](int r) { return c.ll(c.rank, half, r) + l; }, w);
+        if (!ok) break;
+        float acc[EL];
+#pragma unroll
+        for (int j = 0; j < EL; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < DMLB_MAX_WORLD; ++r)
+            if (r < c.world) {
+                if (kWire == DMLB_WIRE_BF16) {
+                    acc[0] += bf16_lo(w[r].x), acc[1] += bf16_hi(w[r].x);
+                    acc[EL - 2] += bf16_lo(w[r].z), acc[EL - 1] += bf16_hi(w[r].z);
+                } else {
+                    acc[0] += __uint_as_float(w[r].x), acc[1] += __uint_as_float(w[r].z);
+                }
+            }
+        const size_t e0 = l * EL;
+#pragma unroll
+        for (int j = 0; j < EL; ++j)
+            if (e0 + j < n) {
+                bucket[e0 + j] = acc[j];
+                if (want_sumsq) part += (double)acc[j] * acc[j];
+            }
+    }
+    if (__syncthreads_or(!ok)) {  // a peer died: nobody trains on a partial sum
+        const float nan = __int_as_float(0x7fc00000);
+        for (size_t e = lo * EL + threadIdx.x; e < hi * EL && e < n; e += kCommThreads) bucket[e] = nan;
+        part = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    if (sumsq_out) {
+        double tot = block_sum(part);
+        if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sumsq_out, tot);
+    }
+    comm_end(c, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // two-shot: slice q (S wire vectors) is reduced by rank q.  CTA b owns vector range [b*per, (b+1)*per) of EVERY slice,
 // so it only ever depends on what the peers' CTA b wrote (per-CTA barriers suffice).
 // kNvls = 1: the reduce-scatter + all-gather pair is done by the switch — multimem.ld_reduce of my slice from the multicast
@@ -367,7 +500,7 @@ allreduce_twoshot_kernel(const __grid_constant__ CommDev c, float *bucket, size_
     constexpr int E = W::kElems;
     const uint32_t s = comm_begin(c);
     if ((int)blockIdx.x >= n_data) {
-        metric_cta(c, s, M);
+        metric_cta<false>(c, s, M);
         comm_end(c, s);
         return;
     }
@@ -476,7 +609,7 @@ extern "C" {
 
 size_t dmlb_comm_arena_bytes(size_t max_message_bytes) {
     size_t m = (max_message_bytes + 255) & ~(size_t)255;
-    return kHeaderBytes + 4 * m;
+    return kHeaderBytes + 4 * m + kLLBytes;
 }
 
 int dmlb_comm_create(void **comm, int world, int rank, void *const *arenas, size_t max_message_bytes) {
@@ -561,7 +694,23 @@ int dmlb_comm_allreduce(void *comm, float *bucket, size_t n, int wire, float sca
                       (algo == 3 || algo == 4 || (algo == 0 && W >= kNvlsMinWorld && bytes >= kNvlsMinBytes));
     if ((algo == 3 || algo == 4) && !nvls && W > 1) return DMLB_ESTATE;
     const bool nvls_rs_only = nvls && algo == 4;
-    const bool oneshot = !nvls && (W == 1 || algo == 1 || (algo == 0 && (bytes <= kOneshotMaxBytes || W <= 2)));
+    const bool oneshot = !nvls && (W == 1 || algo == 1 || algo == 5 || (algo == 0 && (bytes <= kOneshotMaxBytes || W <= 2)));
+    // small messages at W > 1: the LL protocol (no barrier, no peer loads); algo 5 forces the barrier one-shot for A/B runs
+    if (oneshot && W > 1 && algo != 5 && bytes <= kLLMaxPayload) {
+        const int EL = wire == DMLB_WIRE_BF16 ? 4 : 2;
+        const size_t n_lines = (n + EL - 1) / EL;
+        size_t want = (n_lines + kCommThreads - 1) / kCommThreads;  // one line per thread while the grid can grow
+        const size_t cap = (size_t)min(kMaxCtas, sm_count() * 2) - 1;
+        if (want > cap) want = cap;
+        const int n_data = n == 0 ? 0 : (int)(want < 1 ? 1 : want);
+        const int grid = n_data + (metrics ? 1 : 0);
+        const dmlb_step_metrics &Mll = metrics ? *metrics : kNoMetrics;
+        if (wire == DMLB_WIRE_BF16)
+            allreduce_ll_kernel<DMLB_WIRE_BF16><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, n_lines, scale, sumsq, n_data, Mll);
+        else
+            allreduce_ll_kernel<DMLB_WIRE_F32><<<grid, kCommThreads, 0, st>>>(c->dev, bucket, n, n_lines, scale, sumsq, n_data, Mll);
+        return launched();
+    }
     const int kU = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
     const size_t items = oneshot ? nvec : (nvec + W - 1) / W;  // vectors a CTA grid is spread over
     size_t want = (items + (size_t)kCommThreads * kU - 1) / ((size_t)kCommThreads * kU);

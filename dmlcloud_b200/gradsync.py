@@ -75,8 +75,11 @@ class PeerComm:
             self._err_host = torch.zeros(16, dtype=torch.int32).pin_memory()
             dptr = ctypes.c_void_p()
             rc = lib.dmlb_host_device_pointer(self._err_host.data_ptr(), ctypes.byref(dptr))
-            N.check(lib.dmlb_comm_configure(comm, float(timeout_seconds or 0.0), dptr if rc == N.OK else None),
-                    'comm_configure')
+            import os
+
+            # barrier / LL-poll timeout: argument, else DMLB_PEER_TIMEOUT (seconds), else libdmlb's default of 10 minutes
+            timeout = float(timeout_seconds or os.environ.get('DMLB_PEER_TIMEOUT', 0) or 0.0)
+            N.check(lib.dmlb_comm_configure(comm, timeout, dptr if rc == N.OK else None), 'comm_configure')
             self._err_view = self._err_host.numpy()
             if self.world > 1:
                 dist.barrier(group=group)  # every arena is mapped (and zero-filled) before anyone launches

@@ -12,6 +12,15 @@ the arithmetic happens:
       all_reduce on gloo [121-141]                          cells over NVLink peer memory, combine in rank order (K4);
                                                             the vote is the comparison of the count lanes
 
+  (per step, BASELINE configs 2/3: nothing)                 reduce_live(): the same kernel without the reset; in a captured
+                                                            step (graphstep.py) the folds and the exchange ride inside the
+                                                            gradient all-reduce kernel (StepRing / HostFeed below)
+
+Host-side cost is part of the path: python scalars for one cell are combined on the host and travel as one immediate, a
+step's device values ride in ONE fold launch (`DeviceSlab.batching`), a reduce of the same selection reuses prepared launch
+arguments (`_reduce_prepared`), results land in a fixed ring of device-mapped pinned blocks (no copy, no allocation), and
+selections / plans are cached across epochs (`_reduce_all_fast`, `live_selection`).
+
 No CPU path exists for reduced metrics: without CUDA (or without libdmlb.so) tracking a reduced metric raises.
 """
 import ctypes

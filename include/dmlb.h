@@ -196,7 +196,9 @@ int dmlb_comm_set_multicast(void *comm, void *mc_base);
 typedef struct dmlb_step_metrics dmlb_step_metrics; /* defined below, after the metric slab types */
 
 /* in-place averaged all-reduce of an fp32 bucket: bucket = sum_r wire(bucket_r * scale)  (scale = 1/W).
- * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot, 2 two-shot (reduce-scatter + all-gather through
+ * sumsq (optional) receives sum(result^2).  algo: 0 auto, 1 one-shot (LL protocol up to 256 KB of wire bytes: data and
+ * flag pushed together into every peer's arena, no barrier; barrier + peer loads above), 5 one-shot with the barrier
+ * forced at every size (A/B runs), 2 two-shot (reduce-scatter + all-gather through
  * peer loads), 3 NVLS (in-switch reduction: multimem.ld_reduce of this rank's slice + multimem.st of the sum; needs
  * dmlb_comm_set_multicast; the switch's summation order replaces the rank order, see DESIGN.md numerics), 4 NVLS for the
  * reduce-scatter half only (the reduced slices are all-gathered with peer loads, fused with the write-back).

@@ -94,6 +94,7 @@ def main():
                     torch.cuda.synchronize()
                     nvls_result = buf.clone()
             fused_us = time_algo(0)
+            barrier_us = time_algo(5) if wire_bytes <= (256 << 10) else None  # small: LL (auto) vs the barrier one-shot
             big = wire_bytes >= (1 << 20)
             one_us = time_algo(1) if big else None                          # one-shot forced
             pull_us = time_algo(2) if big else None                         # two-shot (peer loads) forced
@@ -137,6 +138,7 @@ def main():
 
             results.append({'bucket': name, 'elements': n, 'wire': wire, 'wire_bytes': wire_bytes,
                             'fused_peer_kernel': entry(fused_us),
+                            'oneshot_barrier_forced': entry(barrier_us) if barrier_us else None,
                             'oneshot_forced': entry(one_us) if one_us else None,
                             'twoshot_forced': entry(pull_us) if pull_us else None,
                             'nvls_forced': entry(nvls_us) if nvls_us else None,

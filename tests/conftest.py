@@ -55,3 +55,5 @@ def free_port():
 
 
 os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+# a protocol bug must fail a test after a minute, not hold the GPU for libdmlb's default ten (spawned ranks inherit this)
+os.environ.setdefault('DMLB_PEER_TIMEOUT', '90')

@@ -60,8 +60,9 @@ def test_pure_host_entry_points():
     assert b'invalid argument' in lib.dmlb_error_string(N.EINVAL)
     assert lib.dmlb_metric_record_words(10) == 22
     m = 1 << 20
-    assert lib.dmlb_comm_arena_bytes(m) == 65536 + 4 * m
-    assert lib.dmlb_comm_arena_bytes(1) == 65536 + 4 * 256
+    ll = 2 * 8 * (2 * (256 << 10) + 2 * (16 + 16 * 1024))  # LL region: [2 halves][8 source ranks][data lines + metric lines]
+    assert lib.dmlb_comm_arena_bytes(m) == 65536 + 4 * m + ll
+    assert lib.dmlb_comm_arena_bytes(1) == 65536 + 4 * 256 + ll
     assert N.launch_count() == 0  # nothing has been launched in this process
 
 

@@ -386,3 +386,40 @@ def test_staged_host_batches_give_the_same_run_as_resident_batches():
         assert torch.equal(a, b) and all(torch.equal(x, y) for x, y in zip(la, lb))
 
     _w1(body)
+
+
+def test_captured_step_refuses_per_group_clipping_it_cannot_honour():
+    """The reference clips per optimizer param group (stage.py:276-279); the captured step's fused sum of squares covers the
+    whole flat bucket, so with two groups it must refuse instead of silently clipping differently."""
+    from dmlcloud_b200 import TrainValStage
+    from dmlcloud_b200.optim import FlatAdam
+    from dmlcloud_b200.pipeline import TrainingPipeline
+
+    class S(TrainValStage):
+        def pre_stage(self):
+            model = make_cnn()
+            self.pipeline.register_model('cnn', model, verbose=False)
+            head = list(model[-1].parameters())
+            body = [p for p in model.parameters() if all(p is not h for h in head)]
+            self.pipeline.register_optimizer('adam', FlatAdam([{'params': body}, {'params': head, 'lr': 1e-4}], lr=1e-3))
+            self.pipeline.register_dataset('train', batches(1, 6, 8), verbose=False)
+            self.pipeline.register_dataset('val', [], verbose=False)
+            self.cuda_graph = True
+
+        def gradient_clip(self):
+            return 1.0
+
+        def step(self, batch):
+            x, y = batch
+            return torch.nn.functional.cross_entropy(self.pipeline.models['cnn'](x.to(self.device)), y.to(self.device))
+
+        def table_columns(self):
+            return [{'name': 'Epoch', 'metric': 'misc/epoch'}]
+
+    def body():
+        p = TrainingPipeline(name='refuse')
+        p.append_stage(S(), max_epochs=1)
+        with pytest.raises(RuntimeError, match='exactly one optimizer param group'):
+            p.run()
+
+    _w1(body)

@@ -191,7 +191,7 @@ def test_fused_allreduce_sizes_and_algorithms(world):
     cases = []
     for n in (1, 7, 9, 4097, 513000):
         for wire in ('fp32', 'bf16'):
-            for algo in (1, 2):  # one-shot, two-shot
+            for algo in (1, 2, 5):  # one-shot (LL protocol up to 256 KB of wire bytes), two-shot, one-shot with the barrier forced
                 cases.append((f'{wire}:n{n}a{algo}', wire, algo, str(n)))
     cases.append(('bf16:big', 'bf16', 0, str(3_963_456)))  # ResNet-18 bucket 3 (15.1 MiB fp32)
     cases.append(('bf16:big2', 'bf16', 2, str(3_963_456)))
@@ -206,7 +206,8 @@ def test_fused_allreduce_odd_and_full_world(world):
     for n in (5, 4099, 600_001):
         for wire in ('fp32', 'bf16'):
             cases += [(f'{wire}:n{n}a2', wire, 2, str(n)), (f'{wire}:n{n}a1', wire, 1, str(n)),
-                      (f'{wire}:n{n}a2b', wire, 2, str(n)), (f'{wire}:n{n}a0', wire, 0, str(n))]
+                      (f'{wire}:n{n}a2b', wire, 2, str(n)), (f'{wire}:n{n}a0', wire, 0, str(n)),
+                      (f'{wire}:n{n}a5', wire, 5, str(n)), (f'{wire}:n{n}a1b', wire, 1, str(n))]
     _check(world, cases, TOL)
 
 

@@ -600,6 +600,91 @@ class TestPipelineHost:
             assert torch.equal(pa, pb)
 
 
+    def test_resume_skips_the_stages_the_interrupted_run_had_finished(self, tmp_path):
+        """a resume restored `stages[idx].current_epoch` but run() still started with stage 0, re-training it
+        and re-tracking into the restored tracker.  The snapshot's stage index now makes run() skip finished stages."""
+        from dmlcloud_b200 import Stage
+        from dmlcloud_b200.pipeline import TrainingPipeline
+
+        ran = []
+
+        class CpuPipeline(TrainingPipeline):
+            def _select_device(self):
+                return torch.device('cpu')
+
+            def _bind_metric_path(self):
+                self.tracker.bind(slab=OracleSlab())
+
+            def resume_run(self):
+                assert self.load_checkpoint('latest')
+
+        class Counting(Stage):
+            def __init__(self, tag):
+                super().__init__()
+                self.tag = tag
+
+            def pre_stage(self):
+                if 'm' not in self.pipeline.models:
+                    self.pipeline.register_model('m', torch.nn.Linear(2, 2), use_ddp=False, verbose=False)
+
+            def run_epoch(self):
+                ran.append((self.tag, self.current_epoch))
+                self.track_reduce(f'{self.tag}/x', torch.tensor(float(self.current_epoch)), prefixed=False)
+
+            def table_columns(self):
+                return [{'name': 'Epoch', 'metric': 'misc/epoch'}]
+
+        def run(root, resume, second_stage_epochs):
+            _dummy_group()
+            try:
+                p = CpuPipeline(name='stages')
+                p.enable_checkpointing(str(root), resume=resume)
+                p.append_stage(Counting('a'), max_epochs=2, name='a')
+                p.append_stage(Counting('b'), max_epochs=second_stage_epochs, name='b')
+                p.run()
+                return p
+            finally:
+                from dmlcloud_b200.util.distributed import deinitialize_torch_distributed
+
+                deinitialize_torch_distributed()
+
+        first = run(tmp_path, False, 1)          # stage a: 2 epochs, stage b: stopped after its 1st epoch
+        assert ran == [('a', 1), ('a', 2), ('b', 1)]
+        del ran[:]
+        resumed = run(first.checkpoint_dir.path, True, 3)
+        assert ran == [('b', 2), ('b', 3)]      # stage a is not run again; stage b continues at its 2nd epoch
+        assert resumed.tracker.epoch == 6 and [v.item() for v in resumed.tracker['a/x'] if v is not None] == [1.0, 2.0]
+
+    def test_live_selection_is_planned_once_per_metric_set_not_once_per_epoch(self):
+        """the 0.8 ms p99 of the per-step exchange was the live selection + layout hash of all 1024
+        metrics being rebuilt after every next_epoch().  The plan object must survive epoch boundaries and change only
+        when the metric set does (or when part of the epoch has already been reduced)."""
+        from dmlcloud_b200.metrics import MetricTracker, Reduction
+
+        t = MetricTracker()
+        t.bind(slab=OracleSlab())
+        for i in range(64):
+            t.register_metric(f'm{i}', Reduction.MEAN)
+            t.track(f'm{i}', float(i))
+        names, plan = t.live_selection()
+        assert len(names) == 64
+        t.next_epoch()
+        for i in range(64):
+            t.track(f'm{i}', 1.0)
+        names2, plan2 = t.live_selection()
+        assert plan2 is plan and names2 is names          # same objects: nothing was re-planned
+        t.reduce_all(prefix='m1')                          # part of the epoch is closed: those metrics leave the live view
+        names3, plan3 = t.live_selection()
+        assert plan3 is not plan and 'm1' not in names3 and 'm2' in names3
+        t.next_epoch()
+        t.register_metric('late', Reduction.SUM)
+        t.track('late', 2)
+        for i in range(64):
+            t.track(f'm{i}', 1.0)
+        names4, plan4 = t.live_selection()
+        assert 'late' in names4 and len(names4) == 65 and plan4 is not plan
+
+
 # ------------------------------------------------------------------------------------------------------ W = 2 over gloo
 def _w2_metrics_worker(rank, world, initfile, outdir):
     init_gloo(rank, world, initfile)
