@@ -833,9 +833,12 @@ def _run_reference(world, steps, warmup, workload, min_seconds):
     from oracle import ref_port, ref_run
 
     if ref_run.available():
-        res = ref_run.run_baseline(world=world, steps=steps, warmup=warmup, total_threads=ref_run.usable_cores(),
-                                   min_seconds=min_seconds, workload=workload)
-        return res
+        try:
+            return ref_run.run_baseline(world=world, steps=steps, warmup=warmup, total_threads=ref_run.usable_cores(),
+                                        min_seconds=min_seconds, workload=workload)
+        except Exception as exc:  # noqa: BLE001 - the installed reference failed to run on this box: say so, time the port
+            print(f'bench.py: oracle/_ref could not be run ({type(exc).__name__}: {exc}); falling back to oracle/ref_port.py',
+                  file=sys.stderr)
     if workload != 'mnist':
         raise SystemExit('bench.py: oracle/_ref (the installed reference) is needed for the ResNet-18 reference arm')
     cores = ref_port.usable_cores()
