@@ -526,10 +526,10 @@ def load_peaks():
 
 def ncu_traffic(kernel_substr):
     """DRAM bytes (read + write) per launch of a kernel from the committed `ncu --set full` summary of the same 1 GiB
-    launch (profiles/r1_bucket_kernels_ncu_full_final.csv, made by profiles/summarize_ncu.py); None if absent."""
+    launch (profiles/r2_bucket_kernels_ncu_full.csv, made by profiles/summarize_ncu.py); None if absent."""
     import csv
 
-    path = ROOT / 'profiles' / 'r1_bucket_kernels_ncu_full_final.csv'
+    path = ROOT / 'profiles' / 'r2_bucket_kernels_ncu_full.csv'
     if not path.exists():
         return None
     rows = list(csv.reader(open(path)))
@@ -611,7 +611,7 @@ def kernel_microbench(dev, peaks):
         'roofline': entry('dmlb_bucket_pack_f32_bf16 (K1, default dispatch)', 6, n, pack,
                           'microbench through the same C-ABI entry point on a 1 GiB fp32 source (cold: > 126 MB L2); '
                           'traffic = dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed '
-                          'ncu --set full capture (profiles/r1_bucket_kernels_ncu_full_final.csv)'),
+                          'ncu --set full capture (profiles/r2_bucket_kernels_ncu_full.csv)'),
         'roofline_more': [entry('dmlb_bucket_pack_f32_bf16_tma (K1 via TMA bulk loads)', 6, n, pack_tma),
                           entry('dmlb_bucket_pack_f32_bf16_regs (K1 via LDG.128 x4 in registers)', 6, n, pack_regs),
                           entry('dmlb_bucket_unpack_bf16_f32 (K2, default dispatch)', 6, n, unpack),

@@ -50,8 +50,14 @@ def test_native_arm_refuses_without_cuda():
 
 
 def test_committed_native_line_carries_the_contract_keys():
-    d = json.loads((ROOT / 'profiles' / 'r1_bench_graph_n1.json').read_text())
-    assert BASE_KEYS | {'clocks', 'gpu_launches', 'roofline', 'cpu_baseline'} <= set(d)
+    d = json.loads((ROOT / 'profiles' / 'r2_bench_mnist_n1.json').read_text())
+    assert BASE_KEYS | {'clocks', 'gpu_launches', 'roofline', 'cpu_baseline', 'windows_ms', 'replicas_identical'} <= set(d)
+    assert d['replicas_identical'] is True and len(d['windows_ms']) >= 5 and len(d['e2e']['windows_ms']) == len(d['windows_ms'])
+    # `value` is the MEDIAN window, and it is not faster than its own fastest window nor slower than its slowest
+    per_step = [w / d['steps'] for w in d['windows_ms']]
+    assert min(per_step) - 1e-4 <= d['ms_per_step'] <= max(per_step) + 1e-4
+    assert d['e2e']['value'] <= d['value'] * 1.02  # the host-fed loop does strictly more work
+    assert d['cpu_baseline']['kind'] == 'reference' and d['config']['kernels_per_step'] == 2
     assert d['gpu_launches'] > 0 and d['n_gpus'] == 1
     assert {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'} <= set(d['e2e'])
     assert d['e2e']['h2d_bytes_per_step'] > 0 and d['e2e']['d2h_bytes_per_step'] > 0
