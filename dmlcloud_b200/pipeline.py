@@ -71,6 +71,7 @@ class TrainingPipeline:
         self.metric_route = 'auto'         # 'auto' | 'peer' | 'collective'
         self.grad_syncs = {}               # model name -> gradsync.GradBucketSync
         self.metric_comm = None
+        self.syncbn_comm = None            # peer communicator of the PeerSyncBatchNorm layers (register_model(sync_bn=True))
         self.compute_stream = None         # dedicated stream all stage work runs on (created in run())
         self._pending_state = {'models': {}, 'optimizers': {}, 'schedulers': {}}  # resumed state awaiting registration
         self._save_policy = {}
@@ -90,7 +91,7 @@ class TrainingPipeline:
             raise ValueError(f'Model with name {name} already exists')
         model = model.to(self.device)  # move first, convert BN second: SyncBN conversion wants device-resident stats
         if sync_bn:
-            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+            model = self._convert_sync_bn(model)
         sync = None
         if use_ddp:
             if self.device is None or self.device.type != 'cuda':
@@ -115,6 +116,21 @@ class TrainingPipeline:
                 route = 'fused NVLink peer kernel' if sync.comm else ('NCCL' if sync.world > 1 else 'single GPU')
                 lines.append(f'    - Gradient exchange: {sync.wire} wire, {route}')
             self.logger.info('\n'.join(lines + [f'    - {model}']))
+
+    def _convert_sync_bn(self, model):
+        """reference pipeline.py:70-71 (`convert_sync_batchnorm`).  With a peer communicator the BatchNorm layers become
+        syncbn.PeerSyncBatchNorm: torch's arithmetic, the per-layer statistics exchange as ONE libdmlb LL all-reduce each
+        way instead of an NCCL all_gather / all_reduce.  Without one (W == 1, no peer mapping, CPU): torch's."""
+        if (self.device is not None and self.device.type == 'cuda' and dist.is_initialized() and dist.get_world_size() > 1
+                and self.metric_route in ('auto', 'peer')):
+            from .gradsync import PeerComm
+            from .syncbn import convert
+
+            if self.syncbn_comm is None:
+                self.syncbn_comm = PeerComm.try_create(self.device, None, max_message_bytes=1 << 20)
+            if self.syncbn_comm is not None:
+                return convert(model, self.syncbn_comm)
+        return torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
 
     def register_optimizer(self, name: str, optimizer, scheduler=None):
         _claim(self.optimizers, 'Optimizer', name, optimizer)
@@ -311,7 +327,7 @@ class TrainingPipeline:
         pass
 
     def _comms(self):
-        return [c for c in [self.metric_comm] + [s.comm for s in self.grad_syncs.values()] if c is not None]
+        return [c for c in [self.metric_comm, self.syncbn_comm] + [s.comm for s in self.grad_syncs.values()] if c is not None]
 
     def poll_comm_errors(self):
         """Raise if a libdmlb collective gave up waiting for a peer.  The kernels report through a word in mapped pinned
