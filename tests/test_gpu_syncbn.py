@@ -76,6 +76,7 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
                 assert torch.equal(b, c), name  # num_batches_tracked
     per_step = (N.launch_count() - launches) / 3
     net.eval()  # evaluation mode: running statistics, no exchange
+    ref.eval()
     before = N.launch_count()
     with torch.no_grad():
         e1, e2 = net(x.detach()), ref(x.detach())
