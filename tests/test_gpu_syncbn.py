@@ -39,7 +39,7 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
     net = convert(copy.deepcopy(ref), comm)
     assert sum(isinstance(m, PeerSyncBatchNorm) for m in net.modules()) == 2
     assert set(net.state_dict()) == set(ref.state_dict())  # same keys: checkpoints are interchangeable
-    worst = 0.0
+    worst, detail = 0.0, {}
     launches = N.launch_count()
     for step in range(3):
         g = torch.Generator().manual_seed(100 * step + rank)
@@ -64,16 +64,17 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
         def rel(a, b):
             return float((a.detach() - b.detach()).abs().max() / b.detach().abs().max().clamp_min(1e-12))
 
-        worst = max(worst, rel(out, rout[lo:hi]), rel(x.grad, gx.grad[lo:hi]))
+        detail[f'out/{step}'], detail[f'dx/{step}'] = rel(out, rout[lo:hi]), rel(x.grad, gx.grad[lo:hi])
         for (name, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
             total = p.grad.clone()
             dist.all_reduce(total)  # the reference's full-batch parameter gradient is the sum of the ranks' local ones
-            worst = max(worst, rel(total, q.grad))
+            detail[f'grad:{name}/{step}'] = rel(total, q.grad)
         for (name, b), (_, c) in zip(net.named_buffers(), ref.named_buffers()):
             if b.dtype.is_floating_point:
-                worst = max(worst, rel(b, c))
+                detail[f'buf:{name}/{step}'] = rel(b, c)
             else:
                 assert torch.equal(b, c), name  # num_batches_tracked
+        worst = max(detail.values())
     per_step = (N.launch_count() - launches) / 3
     net.eval()  # evaluation mode: running statistics, no exchange
     ref.eval()
@@ -82,7 +83,8 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
         e1, e2 = net(x.detach()), ref(x.detach())
     assert N.launch_count() == before  # no exchange in evaluation mode
     assert rel(e1, e2) < 1e-4, rel(e1, e2)  # (running statistics agree to 2e-5 relative, checked above)
-    Path(outdir, f'r{rank}.json').write_text(json.dumps({'worst': worst, 'launches_per_step': per_step}))
+    Path(outdir, f'r{rank}.json').write_text(json.dumps({'worst': worst, 'launches_per_step': per_step,
+                                                         'offenders': {k: v for k, v in detail.items() if v > 2e-5}}))
     dist.barrier()
     comm.close()
     dist.destroy_process_group()
