@@ -175,8 +175,8 @@ def test_snapshot_does_not_block_the_step_loop():
         snap = AsyncSnapshot(d, torch.device('cuda', 0))
         state = {'models': {'m': {'w': torch.randn(1 << 22, device='cuda')}}, 'n': 3, 'cpu': torch.arange(4)}
         big = torch.randn(8192, 8192, device='cuda')
-        for _ in range(20):
-            big = big @ big * 1e-4  # ~ hundreds of ms of queued GPU work
+        for _ in range(40):
+            big = big @ big * 1e-4  # ~0.5 s of queued fp32 GEMMs (the first save also allocates its pinned staging: ms)
         done = torch.cuda.Event()
         snap.save(state, ['latest'])
         done.record()

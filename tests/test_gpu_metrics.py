@@ -167,7 +167,7 @@ class TestMetricTrackerOnGpu:
         torch.cuda.synchronize()
         big = torch.randn(8192, 8192, device='cuda')
         done = torch.cuda.Event()
-        for _ in range(20):
+        for _ in range(40):  # ~0.5 s of queued fp32 GEMMs, far more than the host time of the calls below
             big = big @ big * 1e-4
         for i in range(50):
             t.track('x', big[0, 0])
