@@ -160,19 +160,37 @@ class PeerComm:
                 N.check(lib.dmlb_mc_create(self.world, size, ctypes.byref(fd), ctypes.byref(handle)), 'mc_create')
                 mc_fd, state['mc_handle'] = fd.value, handle.value
             server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            server.settimeout(120)  # accept() gives up when a peer never connects (it died after the vote)
             server.bind(path(self.rank))
             server.listen(self.world)
         except Exception as exc:  # noqa: BLE001
             error = exc
-        self._vote(error is None, 'multicast arena allocation')
+
+        def release_exchange():  # the listening socket, its path and the exported descriptors are only needed for the exchange
+            nonlocal server, own_fd, mc_fd
+            if server is not None:
+                server.close()
+                server = None
+                try:
+                    os.unlink(path(self.rank))
+                except OSError:
+                    pass
+            for f in (own_fd, mc_fd):
+                if f >= 0:
+                    os.close(f)
+            own_fd = mc_fd = -1
+
+        try:
+            self._vote(error is None, 'multicast arena allocation')
+        except RuntimeError:
+            release_exchange()
+            raise
         # every rank sends its arena fd (rank 0 also the multicast fd) to every peer; every rank receives W-1 messages
         arenas = (ctypes.c_void_p * self.world)()
         arenas[self.rank] = own.value
+        received = {}
         try:
-            import array
             import threading
-
-            received = {}
 
             def serve():
                 for _ in range(self.world - 1):
@@ -201,21 +219,14 @@ class PeerComm:
                     h = ctypes.c_uint64(0)
                     N.check(lib.dmlb_mc_import(fds[1], ctypes.byref(h)), 'mc_import')
                     state['mc_handle'] = h.value
-                for f in fds:
-                    os.close(f)
             N.check(lib.dmlb_mc_add_device(state['mc_handle'], dev), 'mc_add_device')
         except Exception as exc:  # noqa: BLE001
             error = exc
         finally:
-            if server is not None:
-                server.close()
-                try:
-                    os.unlink(path(self.rank))
-                except OSError:
-                    pass
-            for f in (own_fd, mc_fd):
-                if f >= 0:
+            for fds in received.values():  # imported or not: the mappings hold their own references
+                for f in fds:
                     os.close(f)
+            release_exchange()
         self._vote(error is None, 'multicast peer mapping')  # (also: every device has joined before anyone binds)
         try:
             mc_ptr = ctypes.c_void_p()
