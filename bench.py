@@ -456,7 +456,7 @@ def native_arm(args):
                    'optimizer': type(pipeline.optimizers['opt']).__name__,
                    'graph_replays': graph.replays if graph is not None else 0,
                    'kernels_per_step': graph.kernels_in_graph if graph is not None else None,
-                   'step_exchange': 'fused into the gradient all-reduce kernel (one peer barrier per step)'
+                   'step_exchange': 'fused into the gradient all-reduce kernel (one launch per step; LL protocol — data and flag pushed together, no separate barrier — for messages <= 256 KB)'
                    if graph is not None and graph.step_metrics is not None else 'separate exchange kernel',
                    'grad_route': sorted(set(sync.last_routes.values())) if graph is None else
                    ['single' if world == 1 else 'peer'],
