@@ -110,6 +110,11 @@ class PeerSyncBatchNorm(torch.nn.modules.batchnorm._BatchNorm):
                                                   factor, self.eps)
         if not x.is_cuda:
             raise ValueError('PeerSyncBatchNorm expects input tensors on a CUDA device (dmlcloud_b200 has no CPU path)')
+        if x.numel() == 0:
+            # torch.nn.SyncBatchNorm filters the rows of ranks with an empty batch out of the gathered statistics with a
+            # boolean mask, i.e. a host synchronisation per layer and step (and not at all while capturing); this layer
+            # never synchronises, so it refuses the case instead of merging a zero-count row (0 * inf) into the statistics
+            raise ValueError('PeerSyncBatchNorm: empty per-rank batch (every rank must contribute at least one sample)')
         return _PeerSyncBN.apply(x, self.weight, self.bias, running_mean, running_var, self.eps, factor, self.comm)
 
 

@@ -86,6 +86,10 @@ def _layer_worker(rank, world, initfile, outdir, channels_last):
         e1, e2 = net(x.detach()), ref(x.detach())
     assert N.launch_count() == before  # no exchange in evaluation mode
     assert rel(e1, e2) < 1e-4, rel(e1, e2)  # (running statistics agree to 2e-5 relative, checked above)
+    net.train()
+    with pytest.raises(ValueError, match='empty per-rank batch'):  # refused on the host, before any collective is issued
+        net(torch.empty(0, 3, 8, 8, device=dev))
+    assert N.launch_count() == before
     Path(outdir, f'r{rank}.json').write_text(json.dumps({'worst': worst, 'launches_per_step': per_step,
                                                          'offenders': {k: v for k, v in detail.items() if v > 2e-5}}))
     dist.barrier()
