@@ -79,12 +79,13 @@ def random_session(seed, world):
     return script
 
 
-def replay(tracker, Reduction, script, rank):
+def replay(tracker, Reduction, script, rank, device=None):
     for op in script:
         if op[0] == 'register':
             tracker.register_metric(op[1], None if op[2] is None else Reduction[op[2]], op[3], op[4])
         elif op[0] == 'track':
-            tracker.track(op[1], torch.tensor(op[2][rank], dtype=getattr(torch, op[3])))
+            value = torch.tensor(op[2][rank], dtype=getattr(torch, op[3]))
+            tracker.track(op[1], value if device is None else value.to(device))
         elif op[0] == 'track_plain':
             tracker.track(op[1], op[2])
         elif op[0] == 'reduce_all':
@@ -93,7 +94,7 @@ def replay(tracker, Reduction, script, rank):
             tracker.next_epoch()
 
 
-def compare(want_tracker, got_tracker, script, seed):
+def compare(want_tracker, got_tracker, script, seed, exact=False):
     kinds = {op[1]: op[2] for op in script if op[0] == 'register'}
     assert got_tracker.epoch == want_tracker.epoch, seed
     assert list(got_tracker.histories) == list(want_tracker.histories), seed
@@ -108,13 +109,17 @@ def compare(want_tracker, got_tracker, script, seed):
             assert isinstance(got, torch.Tensor), where
             got = got.cpu()
             assert got.dtype == want.dtype and got.shape == want.shape, (where, got.dtype, want.dtype, got.shape, want.shape)
-            if not want.dtype.is_floating_point or kinds[name] in ('MIN', 'MAX'):
+            want = want.cpu()
+            if exact or not want.dtype.is_floating_point or kinds[name] in ('MIN', 'MAX'):
                 assert torch.equal(got, want), (where, got, want)
             else:
                 np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6, err_msg=str(where))
 
 
-def run_seeds(seeds, world, rank):
+def run_seeds(seeds, world, rank, device=None, comm=None):
+    """device=None: this repo's MetricTracker over the slab oracle (CPU).  device=cuda: the product — libdmlb's device slab
+    (and `comm`, the peer communicator, at world > 1) — checked against the installed reference AND, bit for bit, against
+    the slab oracle."""
     from dmlcloud_b200.metrics import MetricTracker, Reduction
     from oracle.slab_oracle import OracleSlab
 
@@ -124,10 +129,16 @@ def run_seeds(seeds, world, rank):
         script = random_session(seed, world)
         want = ref.MetricTracker()
         replay(want, ref.Reduction, script, rank)
-        got = MetricTracker()
-        got.bind(slab=OracleSlab())
-        replay(got, Reduction, script, rank)
-        compare(want, got, script, seed)
+        restated = MetricTracker()
+        restated.bind(slab=OracleSlab())
+        replay(restated, Reduction, script, rank)
+        compare(want, restated, script, seed)
+        if device is not None:
+            product = MetricTracker()
+            product.bind(device=device, comm=comm, group=None)
+            replay(product, Reduction, script, rank, device=device)
+            compare(want, product, script, seed)
+            compare(restated, product, script, seed, exact=True)
         checked += sum(len(h) for h in want.histories.values())
     return checked
 
