@@ -161,3 +161,64 @@ class TestSnapshotWriterOnCpu:
         with pytest.raises(ValueError, match='not valid'):
             d.save_state({'n': 1})
         assert not d.has_state('latest')
+
+
+class TestSyncBnConversionHostSide:
+    """syncbn.convert (the counterpart of torch's convert_sync_batchnorm at reference pipeline.py:71) is module surgery and
+    needs no GPU; neither do the cases in which the layer does not exchange anything (evaluation mode, world size 1)."""
+
+    class _Comm:
+        def __init__(self, world):
+            self.world, self.rank = world, 0
+
+    def _net(self):
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4, eps=1e-3, momentum=0.2),
+                                   torch.nn.Sequential(torch.nn.ReLU(), torch.nn.BatchNorm2d(4, affine=False)),
+                                   torch.nn.Flatten(), torch.nn.Linear(4 * 6 * 6, 5), torch.nn.BatchNorm1d(5, track_running_stats=False))
+
+    def test_convert_keeps_parameters_buffers_keys_and_flags(self):
+        from dmlcloud_b200.syncbn import PeerSyncBatchNorm, convert
+
+        net = self._net()
+        net[1].running_mean.uniform_(-1, 1)
+        net.eval()
+        before = dict(net.state_dict())
+        comm = self._Comm(2)
+        out = convert(net, comm)
+        layers = [m for m in out.modules() if isinstance(m, PeerSyncBatchNorm)]
+        assert len(layers) == 3 and all(m.comm is comm for m in layers)
+        assert not any(type(m) in (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d) for m in out.modules())
+        assert list(out.state_dict()) == list(before)
+        for k, v in out.state_dict().items():
+            assert v.data_ptr() == before[k].data_ptr()  # the very same storage: optimizers built before keep working
+        assert (layers[0].eps, layers[0].momentum, layers[0].affine) == (1e-3, 0.2, True)
+        assert layers[1].affine is False and layers[1].weight is None
+        assert layers[2].track_running_stats is False and layers[2].running_mean is None
+        assert not any(m.training for m in layers)
+        assert convert(out, comm) is out and sum(isinstance(m, PeerSyncBatchNorm) for m in out.modules()) == 3  # idempotent
+
+    @pytest.mark.parametrize('world,training', [(1, True), (2, False)])
+    def test_without_an_exchange_the_layer_is_plain_batchnorm(self, world, training):
+        import copy
+
+        from dmlcloud_b200.syncbn import convert
+
+        ref = self._net()[:3]
+        mine = convert(copy.deepcopy(ref), self._Comm(world))
+        ref.train(training)
+        mine.train(training)
+        x = torch.randn(8, 3, 8, 8)
+        for _ in range(2):
+            assert torch.equal(mine(x), ref(x))
+        for (k, a), (_, b) in zip(mine.state_dict().items(), ref.state_dict().items()):
+            assert torch.equal(a, b), k  # running statistics and num_batches_tracked advance alike
+
+    def test_training_with_peers_needs_cuda_inputs(self):
+        from dmlcloud_b200.syncbn import convert
+
+        net = convert(torch.nn.BatchNorm2d(3), self._Comm(2))
+        with pytest.raises(ValueError, match='CUDA'):
+            net(torch.randn(2, 3, 4, 4))
+        with pytest.raises(ValueError, match='at least 2D'):
+            net(torch.randn(3))
