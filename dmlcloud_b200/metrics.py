@@ -202,7 +202,10 @@ class StepRing:
 
 
 class _RingResult:
-    """_PendingResult face over one exchange of a StepRing."""
+    """_PendingResult face over one exchange of a StepRing.  Meant to be read while its exchange is among the latest
+    StepRing.SLOTS ones (the stage replaces `live_metrics` every step): the device reuses the slot SLOTS exchanges later, so
+    a handle kept for longer reports that newer exchange's values instead — never a stale step's, but, if read at the very
+    moment the slot is being rewritten, possibly a mix of the two.  Epoch results (`tracker[name]`) never go through here."""
 
     def __init__(self, ring, k, sync=None):
         self.ring, self.k, self.sync = ring, k, sync
